@@ -1,0 +1,151 @@
+/*
+ * rfdnet_b200.h -- C ABI of librfdnet_b200.so: the B200 (sm_100a) implementation of RfD-Net's
+ * point-cloud hot path.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - all tensors are dense, contiguous, row-major in the shape given in the comment;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call is
+ *     asynchronous on that stream and never synchronises the host;
+ *   - outputs are fully written by the callee (the reference's wrappers rely on torch::zeros;
+ *     here the kernels write every element, or the entry point memsets first where the
+ *     reference semantics need a zero background);
+ *   - return value: RFD_OK (0) or a negative RFD_ERR_* code; rfd_status_string() explains it,
+ *     rfd_last_error() returns the CUDA error text of the last failing call on this thread.
+ *     Unlike the reference (cuda_utils.h:30-39: fprintf + exit(-1)) nothing here terminates
+ *     the process.
+ *
+ * Reference interface each entry point replaces (paths relative to
+ * /root/reference/external/pointnet2_ops_lib/pointnet2_ops/_ext-src/):
+ *   rfd_furthest_point_sampling  <- furthest_point_sampling   include/sampling.h:6,  src/sampling.cpp:66-87
+ *   rfd_gather_points            <- gather_points             include/sampling.h:4,  src/sampling.cpp:15-38
+ *   rfd_gather_points_grad       <- gather_points_grad        include/sampling.h:5,  src/sampling.cpp:40-65
+ *   rfd_ball_query               <- ball_query                include/ball_query.h:4-5, src/ball_query.cpp:8-32
+ *   rfd_group_points             <- group_points              include/group_points.h:4, src/group_points.cpp:12-36
+ *   rfd_group_points_grad        <- group_points_grad         include/group_points.h:5, src/group_points.cpp:38-62
+ *   rfd_three_nn                 <- three_nn                  include/interpolate.h:6,  src/interpolate.cpp:14-40
+ *   rfd_three_interpolate        <- three_interpolate         include/interpolate.h:7-8, src/interpolate.cpp:42-70
+ *   rfd_three_interpolate_grad   <- three_interpolate_grad    include/interpolate.h:9-10, src/interpolate.cpp:71-100
+ *   rfd_query_and_group          <- QueryAndGroup.forward     ../pointnet2_utils.py:302-361 (ball_query + 2x group_points + sub + div + cat)
+ *   rfd_pointwise_mlp_f32        <- Conv{1,2}d(1x1)+BatchNorm(eval)+ReLU(+max_pool2d)  ../pointnet2_modules.py:9-19,237-243
+ *   rfd_three_nn_interpolate     <- PointnetFPModule.forward 3-NN + weights + interpolate  ../pointnet2_modules.py:381-389
+ *   rfd_onet_*                   <- DecoderCBatchNorm.forward /root/reference/models/iscnet/modules/occ_decoder.py:110-122
+ *                                   (+ layers.py:98-107 CResnetBlockConv1d, :226-242 CBatchNorm1d), eval mode
+ *   rfd_make_3d_grid             <- make_3d_grid              /root/reference/external/common.py:157-176 (x box_size, generator.py:92-95)
+ */
+#ifndef RFDNET_B200_H
+#define RFDNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFD_OK 0
+#define RFD_ERR_INVALID_ARGUMENT (-1) /* null pointer, negative size, unsupported combination */
+#define RFD_ERR_UNSUPPORTED_SIZE (-2) /* size outside what the kernels were built for (see each call) */
+#define RFD_ERR_CUDA (-3)             /* a CUDA runtime call or launch failed; see rfd_last_error() */
+#define RFD_ERR_NO_DEVICE (-4)        /* no sm_100 device / wrong architecture */
+
+#define RFD_ABI_VERSION 1
+
+int rfd_abi_version(void);
+const char *rfd_status_string(int status);
+const char *rfd_last_error(void);
+/* sm count, compute capability of the current device; RFD_ERR_NO_DEVICE if it is not compute 10.x */
+int rfd_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* number of kernels launched by this library in this process since load (bench.py's gpu_launches) */
+long long rfd_launch_count(void);
+
+/* ---- (a1) furthest point sampling: xyz (B,N,3) f32 -> idx (B,m) i32.  N <= 196608 per scene.
+ * Bit-exact with the reference kernel incl. its tie-break and the |p|^2 <= 1e-3 skip rule. */
+int rfd_furthest_point_sampling(const float *xyz, int B, int N, int m, int *idx, void *stream);
+
+/* ---- (a2) gather: points (B,C,N), idx (B,M) -> out (B,C,M);  grad: grad_out (B,C,M) -> grad_points (B,C,N) */
+int rfd_gather_points(const float *points, const int *idx, int B, int C, int N, int M, float *out, void *stream);
+int rfd_gather_points_grad(const float *grad_out, const int *idx, int B, int C, int N, int M, float *grad_points,
+                           void *stream);
+
+/* ---- (a3) ball query: new_xyz (B,M,3), xyz (B,N,3) -> idx (B,M,nsample) i32; nsample <= 1024 */
+int rfd_ball_query(const float *new_xyz, const float *xyz, int B, int N, int M, float radius, int nsample, int *idx,
+                   void *stream);
+
+/* ---- (a4) group: points (B,C,N), idx (B,M,S) -> out (B,C,M,S);  grad: (B,C,M,S) -> (B,C,N) */
+int rfd_group_points(const float *points, const int *idx, int B, int C, int N, int M, int S, float *out,
+                     void *stream);
+int rfd_group_points_grad(const float *grad_out, const int *idx, int B, int C, int N, int M, int S,
+                          float *grad_points, void *stream);
+
+/* ---- (a5) fused ball query + grouping.
+ * xyz (B,N,3), new_xyz (B,M,3), features (B,C,N) or NULL (C=0)
+ *   -> new_features (B, (use_xyz?3:0)+C, M, S) ; grouped_xyz (B,3,M,S) or NULL ; idx (B,M,S) or NULL.
+ * grouped xyz = (xyz[idx] - new_xyz) and, when normalize_xyz, * (1.0f/radius) -- the CUDA reference
+ * (torch `tensor /= python_float` lowers to a multiply by the f32 reciprocal).  nsample <= 128. */
+int rfd_query_and_group(const float *xyz, const float *new_xyz, const float *features, int B, int N, int M, int C,
+                        float radius, int nsample, int use_xyz, int normalize_xyz, float *new_features,
+                        float *grouped_xyz, int *idx, void *stream);
+
+/* ---- (a7) three_nn: unknown (B,n,3), known (B,m,3) -> dist2 (B,n,3) f32 (squared), idx (B,n,3) i32 */
+int rfd_three_nn(const float *unknown, const float *known, int B, int n, int m, float *dist2, int *idx,
+                 void *stream);
+/* ---- (a8) three_interpolate: points (B,C,m), idx (B,n,3), weight (B,n,3) -> out (B,C,n); and its grad */
+int rfd_three_interpolate(const float *points, const int *idx, const float *weight, int B, int C, int m, int n,
+                          float *out, void *stream);
+int rfd_three_interpolate_grad(const float *grad_out, const int *idx, const float *weight, int B, int C, int n,
+                               int m, float *grad_points, void *stream);
+/* fused FP front end: 3-NN + sqrt + 1/(d+1e-8) normalised weights + interpolation, writing into the first
+ * C channels of out (B,Ctot,n) (the skip features are concatenated by the caller into channels C..Ctot). */
+int rfd_three_nn_interpolate(const float *unknown, const float *known, const float *known_feats, int B, int n,
+                             int m, int C, int Ctot, float *out, void *stream);
+
+/* ---- (a6/a9/a10/a11) pointwise (1x1 conv) layer in fp32, BN folded (eval), optional ReLU and max-pool.
+ * x (B,Cin,L), W (Cout,Cin) row-major, scale/shift (Cout) [y = relu?(scale*(W.x)+shift)],
+ * pool = 1: y (B,Cout,L); pool = S>1: max over each run of S consecutive positions -> y (B,Cout,L/S).
+ * residual (B,Cout,L) or NULL is added after the affine (before ReLU is NOT applied to it: y = act(...) + res). */
+int rfd_pointwise_mlp_f32(const float *x, const float *W, const float *scale, const float *shift,
+                          const float *residual, int relu, int pool, int B, int Cin, int Cout, int L, float *y,
+                          void *stream);
+
+/* ---- (a13) occupancy query lattice: out (R^3,3) f32 = box_size * linspace(-0.5,0.5,R) on each axis, z fastest */
+int rfd_make_3d_grid(int R, float box_size, float *out, void *stream);
+
+/* ---- (a12) ONet decoder (DecoderCBatchNorm, eval mode), hidden = 256, n_blocks = 5.
+ * Step 1 (once per checkpoint): pack the fp32 fc weights into the device layout the kernel streams:
+ *   fc_w (10,256,256) f32 = [blocks.0.fc_0, blocks.0.fc_1, blocks.1.fc_0, ...].weight  ([out][in])
+ *   -> packed (rfd_onet_packed_bytes(1) bytes): bf16, one 32-KB image per (layer, 64-wide K panel) of the
+ *      UMMA K-major 128B-swizzled B operand, in consumption order.
+ * Step 2 (per batch of objects): conditional-BN tables (tiny fp32 GEMMs)
+ *   c (B,c_dim); gamma_w/beta_w (11,256,c_dim) and gamma_b/beta_b (11,256) = conv_gamma/conv_beta of
+ *   [blocks.0.bn_0, blocks.0.bn_1, ..., blocks.4.bn_1, bn]; run_mean/run_var (11,256); eps;
+ *   fc_bias (10,256) biases of the fc layers above; x_bias (B,256) = fc_p.bias + fc_z(z) (+ fc_z.bias)
+ *   -> aff (B, rfd_onet_aff_floats()) f32: per object [11][2][256] scale a / shift c with
+ *      relu(CBN_l(x_true)) == relu(a * x_acc + c)  (x_acc = bias-free accumulator held by the kernel),
+ *      followed by the 256 x_bias values.
+ * Step 3: logits (B,T) = decoder(p).  p is (B,T,3) with p_batch_stride = T*3 floats, or one shared
+ *   (T,3) lattice for every object with p_batch_stride = 0.
+ * nsplit = 1: bf16 operands, fp32 accumulation/residual (config 4).  nsplit = 3 (bf16x3) is reserved:
+ * RFD_ERR_UNSUPPORTED_SIZE for now; the fp32-exact results come from rfd_onet_decode_f32. */
+size_t rfd_onet_packed_bytes(int nsplit);
+size_t rfd_onet_aff_floats(void);
+int rfd_onet_pack_weights(const float *fc_w, int nsplit, void *packed, void *stream);
+int rfd_onet_cbn_tables(const float *c, int B, int c_dim, const float *gamma_w, const float *gamma_b,
+                        const float *beta_w, const float *beta_b, const float *run_mean, const float *run_var,
+                        float eps, const float *fc_bias, const float *x_bias, float *aff, void *stream);
+int rfd_onet_decode(const float *p, long long p_batch_stride, int B, int T, const float *fc_p_w /*(256,3)*/,
+                    const void *packed, int nsplit, const float *aff, const float *fc_out_w /*(256)*/,
+                    float fc_out_b, float *logits, void *stream);
+/* fp32 CUDA-core implementation of the same decoder (exact path, slow): the 1e-4 parity claim, the
+ * on-GPU yardstick for the tensor-core path, and the "fp32" row of the benchmark.
+ * workspace: at least 2*256*T*4 bytes (one object); larger = more objects per pass. */
+int rfd_onet_decode_f32(const float *p, long long p_batch_stride, int B, int T, const float *fc_p_w,
+                        const float *fc_w /*(10,256,256)*/, const float *aff, const float *fc_out_w,
+                        float fc_out_b, float *logits, float *workspace, size_t workspace_bytes, void *stream);
+/* tcgen05 plumbing self-test: D (128,256) f32 = bf16(A (128,64)) . bf16(B (256,64))^T */
+int rfd_umma_selftest(const float *A, const float *B, float *D, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFDNET_B200_H */

@@ -1,0 +1,306 @@
+// fps.cu -- furthest point sampling for sm_100a.
+//
+// Replaces furthest_point_sampling_kernel (reference _ext-src/src/sampling_gpu.cu:69-173, launcher :175-229,
+// wrapper sampling.cpp:66-87).  The reference runs ONE 512-thread CTA per scene and, per round, streams all N
+// points plus the (B,N) `temp` scratch through that single SM, with a 9-stage shared-memory tree behind 10
+// __syncthreads.  Here a scene is owned by a thread-block CLUSTER (up to 16 CTAs = 16 SMs):
+//   * every thread keeps its points' xyz and running min-distance in REGISTERS for the whole kernel
+//     (no `temp` tensor exists; HBM traffic is the compulsory 12*N bytes in + 4*m bytes out);
+//   * per round: register update -> warp arg-max with two redux.sync -> one __syncthreads -> CTA arg-max ->
+//     the CTA winner (key + xyz) is pushed to every peer CTA's shared memory over DSMEM and signalled with a
+//     remote mbarrier arrive (release.cluster); peers wait on their local mbarrier (acquire.cluster).
+//     No cluster-wide barrier and no global-memory round trip sits on the serial chain.
+//
+// Bit-exactness with the reference:
+//   * arithmetic order of the sm_100 build of the reference (cuobjdump): mag = fma(z,z,fma(x,x,y*y)),
+//     skip iff (double)mag <= 1e-3; d = fma(dz,dz,fma(dx,dx,dy*dy)) with dx = p - p_old; temp = fminf(d,temp);
+//   * arg-max tie-break.  Reference thread t (block size bs = opt_n_threads(N), cuda_utils.h:15-19) scans
+//     k = t, t+bs, ... with a strict '>' (first max wins, :108-109); the tree (:115-168, __update :59-65) keeps
+//     the LOWER slot on ties at each stage, stage strides bs/2 ... 1.  The overall winner among equal values
+//     is therefore the candidate with the smallest  rank(k) = bitrev_{log2 bs}(k mod bs) * ceil(N/bs) + k div bs.
+//     We reduce the 64-bit key (float_bits(value) : ~rank) with max, which is order independent.
+//     A thread here owns k = g, g+T, g+2T, ... (T = threads per cluster, a multiple of bs), i.e. one slot in
+//     ascending k -- so the in-register strict '>' scan is already rank-ordered;
+//   * "no candidate" (all points skipped) reproduces the reference result old = 0.
+#include "common.cuh"
+
+namespace rfd {
+
+constexpr int FPS_THREADS = 512;
+constexpr int FPS_WARPS = FPS_THREADS / 32;
+constexpr int FPS_MAX_CS = 16;
+constexpr int FPS_MAX_PPT = 24;
+
+struct __align__(16) FpsRec {
+  uint32_t hi, lo;  // key: value bits, ~rank  (0,0 = no candidate)
+  int k, pad0;
+  float x, y, z, pad1;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+
+// warp-level arg-max over up to 32 records in shared memory; returns the winning record in every lane
+__device__ __forceinline__ FpsRec fps_pick(const FpsRec *recs, int n, int lane) {
+  uint32_t hi = 0, lo = 0;
+  if (lane < n) {
+    const uint2 h = *reinterpret_cast<const uint2 *>(&recs[lane]);
+    hi = h.x;
+    lo = h.y;
+  }
+  const uint32_t hmax = __reduce_max_sync(0xffffffffu, hi);
+  const uint32_t lmax = __reduce_max_sync(0xffffffffu, hi == hmax ? lo : 0u);
+  const uint32_t win = __ballot_sync(0xffffffffu, lane < n && hi == hmax && lo == lmax);
+  const int src = __ffs(win) - 1;
+  const uint4 a = *reinterpret_cast<const uint4 *>(&recs[src]);
+  const float4 b = *(reinterpret_cast<const float4 *>(&recs[src]) + 1);
+  FpsRec r;
+  r.hi = a.x; r.lo = a.y; r.k = (int)a.z; r.pad0 = 0;
+  r.x = b.x; r.y = b.y; r.z = b.z; r.pad1 = 0.f;
+  return r;
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(FPS_THREADS, 1)
+fps_kernel(const float *__restrict__ xyz_all, int N, int m, int bs_log2, int Q, int CS, int *__restrict__ idx_all) {
+  extern __shared__ float4 s_pts[];  // [PPT][FPS_THREADS] this CTA's points (winner looks its xyz up here)
+  __shared__ FpsRec s_warp[2][FPS_WARPS];
+  __shared__ FpsRec s_cta[2][FPS_MAX_CS];
+  __shared__ __align__(8) uint64_t s_mbar[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = (CS > 1) ? cluster_ctarank() : 0u;
+  const int scene = blockIdx.x / CS;
+  const float *__restrict__ xyz = xyz_all + (size_t)scene * N * 3;
+  int *__restrict__ idx_out = idx_all + (size_t)scene * m;
+  const int T = CS * FPS_THREADS;
+  const int g = (int)rank * FPS_THREADS + tid;
+
+  if (CS > 1) {
+    if (tid == 0) {
+      mbar_init(smem_u32(&s_mbar[0]), (uint32_t)CS);
+      mbar_init(smem_u32(&s_mbar[1]), (uint32_t)CS);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_sync_all();  // barriers initialised + every CTA of the cluster is resident before any DSMEM access
+  }
+
+  float px[PPT], py[PPT], pz[PPT], td[PPT];
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    const int k = g + i * T;
+    float x = 0.f, y = 0.f, z = 0.f, t = -INFINITY;
+    if (k < N) {
+      x = __ldg(xyz + (size_t)k * 3 + 0);
+      y = __ldg(xyz + (size_t)k * 3 + 1);
+      z = __ldg(xyz + (size_t)k * 3 + 2);
+      float mag = __fmul_rn(y, y);
+      mag = __fmaf_rn(x, x, mag);
+      mag = __fmaf_rn(z, z, mag);
+      // reference :101 `if (mag <= 1e-3) continue;` -- float promoted to double against a double literal.
+      // A skipped point is never a candidate: td = -inf makes fminf(d, td) = -inf, never > best (-1).
+      t = ((double)mag <= 1e-3) ? -INFINITY : 1e10f;
+    }
+    px[i] = x; py[i] = y; pz[i] = z; td[i] = t;
+    s_pts[i * FPS_THREADS + tid] = make_float4(x, y, z, 0.f);
+  }
+  const float p0x = __ldg(xyz + 0), p0y = __ldg(xyz + 1), p0z = __ldg(xyz + 2);
+  float x1 = p0x, y1 = p0y, z1 = p0z;  // old = 0
+  if (g == 0 && m > 0) idx_out[0] = 0;
+  uint32_t phases = 0;
+  const uint32_t bs_mask = (1u << bs_log2) - 1u;
+
+  for (int j = 1; j < m; ++j) {
+    const int par = j & 1;
+    float best = -1.f;
+    int besti = 0;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const float d = sqdist_yxz(px[i] - x1, py[i] - y1, pz[i] - z1);
+      const float d2 = fminf(d, td[i]);
+      td[i] = d2;
+      const bool gt = d2 > best;
+      besti = gt ? i : besti;
+      best = gt ? d2 : best;
+    }
+    uint32_t hi = 0u, lo = 0u;
+    const int k = g + besti * T;
+    if (best >= 0.f) {
+      const uint32_t slot = (uint32_t)k & bs_mask;
+      const uint32_t rev = bs_log2 ? (__brev(slot) >> (32 - bs_log2)) : 0u;
+      const uint32_t rk = rev * (uint32_t)Q + ((uint32_t)k >> bs_log2);
+      hi = __float_as_uint(best);
+      lo = 0xffffffffu - rk;
+    }
+    {
+      const uint32_t hmax = __reduce_max_sync(0xffffffffu, hi);
+      const uint32_t lmax = __reduce_max_sync(0xffffffffu, hi == hmax ? lo : 0u);
+      const bool none = (hmax | lmax) == 0u;
+      const bool win = none ? (lane == 0) : (hi == hmax && lo == lmax);
+      if (win) {
+        const float4 p = s_pts[besti * FPS_THREADS + tid];
+        uint4 *dst = reinterpret_cast<uint4 *>(&s_warp[par][warp]);
+        dst[0] = make_uint4(hmax, lmax, (uint32_t)k, 0u);
+        reinterpret_cast<float4 *>(dst)[1] = p;
+      }
+    }
+    __syncthreads();
+    FpsRec r;
+    if (CS == 1) {
+      r = fps_pick(s_warp[par], FPS_WARPS, lane);
+    } else {
+      if (warp == 0) {
+        const FpsRec c = fps_pick(s_warp[par], FPS_WARPS, lane);
+        if (lane < CS) {
+          const uint32_t dst = mapa_u32(smem_u32(&s_cta[par][rank]), (uint32_t)lane);
+          st_cluster_v4(dst, c.hi, c.lo, (uint32_t)c.k, 0u);
+          st_cluster_v4(dst + 16, __float_as_uint(c.x), __float_as_uint(c.y), __float_as_uint(c.z), 0u);
+          mbar_arrive_remote_release(mapa_u32(smem_u32(&s_mbar[par]), (uint32_t)lane));
+        }
+      }
+      mbar_wait_acquire_cluster(smem_u32(&s_mbar[par]), (phases >> par) & 1u);
+      phases ^= (1u << par);
+      r = fps_pick(s_cta[par], CS, lane);
+    }
+    int old;
+    if ((r.hi | r.lo) == 0u) {  // no candidate anywhere: reference leaves besti = 0 in every thread
+      old = 0; x1 = p0x; y1 = p0y; z1 = p0z;
+    } else {
+      old = r.k; x1 = r.x; y1 = r.y; z1 = r.z;
+    }
+    if (g == 0) idx_out[j] = old;
+  }
+  if (CS > 1) cluster_sync_all();  // no CTA may exit while a peer can still write into its shared memory
+}
+
+template <int PPT>
+static int launch_fps(const float *xyz, int B, int N, int m, int bs_log2, int Q, int CS, int *idx,
+                      cudaStream_t stream, bool probe_only, int *max_clusters) {
+  auto kern = fps_kernel<PPT>;
+  const size_t smem = (size_t)PPT * FPS_THREADS * sizeof(float4);
+  RFD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fps attr smem");
+  if (CS > 8)
+    RFD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "fps attr cluster");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * CS));
+  cfg.blockDim = dim3(FPS_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (probe_only) {
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    *max_clusters = n;
+    return RFD_OK;
+  }
+  RFD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, bs_log2, Q, CS, idx), "fps launch");
+  RFD_CHECK_LAUNCH("fps_kernel");
+  return RFD_OK;
+}
+
+static int dispatch_fps(int ppt, const float *xyz, int B, int N, int m, int bs_log2, int Q, int CS, int *idx,
+                        cudaStream_t stream, bool probe, int *maxc) {
+#define RFD_FPS_CASE(P) \
+  if (ppt <= P) return launch_fps<P>(xyz, B, N, m, bs_log2, Q, CS, idx, stream, probe, maxc);
+  RFD_FPS_CASE(1) RFD_FPS_CASE(2) RFD_FPS_CASE(3) RFD_FPS_CASE(4) RFD_FPS_CASE(6) RFD_FPS_CASE(8)
+  RFD_FPS_CASE(10) RFD_FPS_CASE(12) RFD_FPS_CASE(16) RFD_FPS_CASE(20) RFD_FPS_CASE(24)
+#undef RFD_FPS_CASE
+  return RFD_ERR_UNSUPPORTED_SIZE;
+}
+
+// reference cuda_utils.h:15-19 (evaluated with the same double arithmetic)
+static int ref_opt_n_threads(int work_size) {
+  const int pow_2 = (int)(std::log((double)work_size) / std::log(2.0));
+  int v = 1 << pow_2;
+  if (v > 512) v = 512;
+  if (v < 1) v = 1;
+  return v;
+}
+
+int fps_plan(int N, int B, int num_sms, int *cs_out, int *ppt_out) {
+  const int need = (N + FPS_THREADS - 1) / FPS_THREADS;  // point slots per thread column
+  int cs = 1;
+  if (N > 8192) {
+    while (cs < FPS_MAX_CS && (need + cs - 1) / cs > 10) cs *= 2;
+    // oversubscribed GPU: prefer fewer, fatter CTAs per scene as long as the points still fit in registers
+    while (cs > 1 && (long long)B * cs > num_sms && (need + cs / 2 - 1) / (cs / 2) <= FPS_MAX_PPT) cs /= 2;
+  }
+  while (cs < FPS_MAX_CS && (need + cs - 1) / cs > FPS_MAX_PPT) cs *= 2;
+  const int ppt = (need + cs - 1) / cs;
+  if (ppt > FPS_MAX_PPT) return RFD_ERR_UNSUPPORTED_SIZE;
+  *cs_out = cs;
+  *ppt_out = ppt;
+  return RFD_OK;
+}
+
+}  // namespace rfd
+
+extern "C" int rfd_furthest_point_sampling(const float *xyz, int B, int N, int m, int *idx, void *stream) {
+  using namespace rfd;
+  if (B < 0 || N < 1 || m < 0 || (B > 0 && (!xyz || (m > 0 && !idx)))) return RFD_ERR_INVALID_ARGUMENT;
+  if (B == 0 || m == 0) return RFD_OK;
+  int dev = 0, sms = 148;
+  RFD_CHECK_CUDA(cudaGetDevice(&dev), "fps getdevice");
+  RFD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "fps sms");
+  int cs = 1, ppt = 1;
+  int rc = fps_plan(N, B, sms, &cs, &ppt);
+  if (rc != RFD_OK) return rc;
+  const int bs = ref_opt_n_threads(N);
+  int bs_log2 = 0;
+  while ((1 << bs_log2) < bs) ++bs_log2;
+  const int Q = (N + bs - 1) / bs;
+  cudaStream_t st = as_stream(stream);
+  // a 16-CTA (non-portable) cluster may not be schedulable on every part/partition: fall back to 8
+  while (cs > 8) {
+    int maxc = 0;
+    rc = dispatch_fps(ppt, xyz, B, N, m, bs_log2, Q, cs, idx, st, true, &maxc);
+    if (rc != RFD_OK) return rc;
+    if (maxc > 0) break;
+    cs /= 2;
+    ppt = ((N + FPS_THREADS - 1) / FPS_THREADS + cs - 1) / cs;
+    if (ppt > FPS_MAX_PPT) return RFD_ERR_UNSUPPORTED_SIZE;
+  }
+  return dispatch_fps(ppt, xyz, B, N, m, bs_log2, Q, cs, idx, st, false, nullptr);
+}

@@ -1,0 +1,562 @@
+// onet_decoder.cu -- the ONet occupancy decoder (DecoderCBatchNorm, eval mode) for sm_100a.
+//
+// Reference: /root/reference/models/iscnet/modules/occ_decoder.py:72-122 (DecoderCBatchNorm.forward :110-122),
+// layers.py:51-107 (CResnetBlockConv1d.forward :98-107), layers.py:193-242 (CBatchNorm1d.forward :226-242);
+// driver generator.py:123-143 (eval_points, ONE object of 32768 points per call, 11 conv launches + 22 CBN
+// convs + elementwise kernels per object, then a .cpu() sync).
+//
+//   net = fc_p(p) + fc_z(z)                                   (3 -> 256)
+//   5 x { net = net + fc_1(relu(cbn_1(fc_0(relu(cbn_0(net, c))), c))) }   (256 -> 256 -> 256)
+//   out = fc_out(relu(cbn(net, c)))                            (256 -> 1)
+//   cbn_l(x, c)[ch] = gamma_l(c)[ch] * (x[ch] - mean_l[ch]) / sqrt(var_l[ch] + eps) + beta_l(c)[ch]   (eval mode)
+//
+// Here the whole decoder for a tile of 128 query points is ONE pass of a persistent, warp-specialised kernel:
+//   * the fp32 residual stream x (128 x 256) and the hidden pre-activation net (128 x 256) live in TENSOR MEMORY
+//     (2 x 256 columns = the whole 512-column TMEM of the SM); fc_1 accumulates straight onto x, so the residual
+//     add costs nothing and never leaves fp32;
+//   * the ten 256x256 GEMMs run on tcgen05.mma (M=128, N=256, K=16, bf16 x bf16 -> f32), issued by one thread;
+//   * conv biases are never added in the kernel: they are folded, together with the conditional-BN statistics,
+//     into one per-object/per-layer/per-channel affine (a, c) so that relu(cbn_l(x_true)) = relu(a*x_acc + c)
+//     (rfd_onet_cbn_tables).  The epilogue warps read the accumulator with tcgen05.ld, apply that affine + ReLU,
+//     round to bf16 and write the next layer's A operand into shared memory in the UMMA K-major 128B-swizzled
+//     layout, 64-channel panel by panel; the MMA of the next layer starts on a panel as soon as it is complete;
+//   * weights (10 x 256 x 256 bf16, pre-swizzled by rfd_onet_pack_weights) stream from L2 through a 3-stage ring
+//     of 32-KB bulk copies (cp.async.bulk, mbarrier complete_tx) issued by a dedicated producer warp, which also
+//     prefetches the next tile's affine table;
+//   * fc_p (K = 3) and fc_out (N = 1) are evaluated in fp32 on the CUDA cores inside the same kernel.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace rfd {
+
+constexpr int DEC_H = 256;
+constexpr int DEC_LAYERS = 10;
+constexpr int DEC_CBN = 11;
+constexpr int DEC_TILE_M = 128;
+constexpr int DEC_KP = 4;
+constexpr int DEC_PANEL_A = DEC_TILE_M * 128;   // 16384 B : 128 rows x 64 bf16
+constexpr int DEC_STAGE_B = DEC_H * 128;        // 32768 B : 256 rows x 64 bf16
+constexpr int DEC_NSTAGE = 3;
+constexpr int DEC_AFF_FLOATS = DEC_CBN * 2 * DEC_H + DEC_H;  // 5888 floats / object (a,c per layer + x_bias)
+constexpr int DEC_AFF_BYTES = DEC_AFF_FLOATS * 4;             // 23552
+constexpr int DEC_THREADS = 320;                // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int DEC_EPI_WARPS = 8;
+
+// shared memory map (offsets from a 1024-B aligned base)
+constexpr int SM_AH = 0;
+constexpr int SM_W = SM_AH + DEC_KP * DEC_PANEL_A;              // 65536
+constexpr int SM_AFF = SM_W + DEC_NSTAGE * DEC_STAGE_B;         // 163840
+constexpr int SM_WP = SM_AFF + 2 * DEC_AFF_BYTES;               // 210944
+constexpr int SM_WOUT = SM_WP + 3 * DEC_H * 4;                  // 214016
+constexpr int SM_OUT = SM_WOUT + DEC_H * 4;                     // 215040
+constexpr int SM_BAR = SM_OUT + 2 * DEC_TILE_M * 4;             // 216064
+constexpr int SM_TOTAL = SM_BAR + 256;                          // 216320
+constexpr int DEC_SMEM_BYTES = SM_TOTAL + 1024;                 // + alignment slack
+
+struct DecBars {
+  uint64_t w_full[DEC_NSTAGE];
+  uint64_t w_empty[DEC_NSTAGE];
+  uint64_t aff_full[2];
+  uint64_t aff_empty[2];
+  uint64_t a_ready[DEC_KP];
+  uint64_t acc_ready;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(DEC_THREADS, 1)
+onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const float *__restrict__ fc_p_w,
+                   const uint8_t *__restrict__ packed, const float *__restrict__ aff_all,
+                   const float *__restrict__ fc_out_w, float fc_out_b, float *__restrict__ logits, int num_tiles,
+                   int tiles_per_obj) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *s_ah = smem + SM_AH;
+  uint8_t *s_w = smem + SM_W;
+  float *s_aff = reinterpret_cast<float *>(smem + SM_AFF);
+  float *s_wp = reinterpret_cast<float *>(smem + SM_WP);      // [3][256]
+  float *s_wout = reinterpret_cast<float *>(smem + SM_WOUT);  // [256]
+  float *s_out = reinterpret_cast<float *>(smem + SM_OUT);    // [2][128]
+  DecBars *bars = reinterpret_cast<DecBars *>(smem + SM_BAR);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) {
+    for (int i = 0; i < DEC_NSTAGE; ++i) { umma::mbar_init(&bars->w_full[i], 1); umma::mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->aff_full[i], 1); umma::mbar_init(&bars->aff_empty[i], DEC_EPI_WARPS); }
+    for (int i = 0; i < DEC_KP; ++i) umma::mbar_init(&bars->a_ready[i], DEC_EPI_WARPS);
+    umma::mbar_init(&bars->acc_ready, 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 1) umma::tmem_alloc(&bars->tmem_base, 512);
+  for (int e = tid; e < 3 * DEC_H; e += DEC_THREADS) {
+    const int k = e / DEC_H, o = e % DEC_H;
+    s_wp[e] = __ldg(fc_p_w + o * 3 + k);  // torch layout (256,3) -> [3][256]
+  }
+  for (int e = tid; e < DEC_H; e += DEC_THREADS) s_wout[e] = __ldg(fc_out_w + e);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tmem_x = tmem_base, tmem_n = tmem_base + DEC_H;
+
+  if (warp == 0) {
+    // ===================== producer: weight ring + affine-table prefetch =====================
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        if (it == 0) {
+          umma::mbar_arrive_expect_tx(&bars->aff_full[0], DEC_AFF_BYTES);
+          umma::bulk_g2s(s_aff, aff_all + (size_t)(tile / tiles_per_obj) * DEC_AFF_FLOATS, DEC_AFF_BYTES,
+                         &bars->aff_full[0]);
+        }
+        for (int s = 0; s < DEC_LAYERS * DEC_KP; ++s) {
+          if (s == 8) {
+            const int next = tile + gridDim.x;
+            if (next < num_tiles) {
+              const int nb = (it + 1) & 1;
+              const uint32_t n = (uint32_t)(it + 1) >> 1;  // use count of that buffer
+              umma::mbar_wait(&bars->aff_empty[nb], (n & 1u) ^ 1u);
+              umma::mbar_arrive_expect_tx(&bars->aff_full[nb], DEC_AFF_BYTES);
+              umma::bulk_g2s(s_aff + nb * DEC_AFF_FLOATS, aff_all + (size_t)(next / tiles_per_obj) * DEC_AFF_FLOATS,
+                             DEC_AFF_BYTES, &bars->aff_full[nb]);
+            }
+          }
+          umma::mbar_wait(&bars->w_empty[st], ph ^ 1u);
+          umma::mbar_arrive_expect_tx(&bars->w_full[st], DEC_STAGE_B);
+          umma::bulk_g2s(s_w + st * DEC_STAGE_B, packed + (size_t)s * DEC_STAGE_B, DEC_STAGE_B, &bars->w_full[st]);
+          if (++st == DEC_NSTAGE) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma::make_idesc_bf16_f32(DEC_TILE_M, DEC_H);
+      const uint32_t ah_addr = umma::smem_u32(s_ah), w_addr = umma::smem_u32(s_w);
+      uint32_t st = 0, ph = 0, layer_count = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int l = 0; l < DEC_LAYERS; ++l, ++layer_count) {
+          const uint32_t d = (l & 1) ? tmem_x : tmem_n;  // fc_0 -> net (fresh), fc_1 -> accumulate onto x
+          for (int kp = 0; kp < DEC_KP; ++kp) {
+            umma::mbar_wait(&bars->a_ready[kp], layer_count & 1u);
+            umma::mbar_wait(&bars->w_full[st], ph);
+            umma::tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = umma::make_desc_k_sw128(ah_addr + kp * DEC_PANEL_A + k * 32);
+              const uint64_t bd = umma::make_desc_k_sw128(w_addr + st * DEC_STAGE_B + k * 32);
+              umma::mma_bf16_ss(d, ad, bd, idesc, (l & 1) ? 1u : (uint32_t)((kp | k) != 0));
+            }
+            umma::mma_commit(&bars->w_empty[st]);  // frees the weight slot when these MMAs retire
+            if (kp == DEC_KP - 1) umma::mma_commit(&bars->acc_ready);
+            if (++st == DEC_NSTAGE) { st = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (8): TMEM -> affine+ReLU -> bf16 A panels =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;     // TMEM lane quarter this warp may access
+    const int hsel = ew >> 2;   // which 32-column half of every 64-column panel
+    const int r = q * 32 + lane;  // row of the tile owned by this thread
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t layer_count = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int obj = tile / tiles_per_obj;
+      const int t = (tile - obj * tiles_per_obj) * DEC_TILE_M + r;
+      const bool valid = t < T;
+      const int ab = it & 1;
+      umma::mbar_wait(&bars->aff_full[ab], ((uint32_t)it >> 1) & 1u);
+      const float *aff = s_aff + ab * DEC_AFF_FLOATS;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (valid) {
+        const float *pp = p + (size_t)obj * p_stride + (size_t)t * 3;
+        px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
+      }
+      // ---- E0: x0 = fc_p(p) + (fc_p.bias + fc_z(z)) in fp32 -> TMEM ; h0 = relu(a0*x0 + c0) -> A panels
+      {
+        const float *xb = aff + DEC_CBN * 2 * DEC_H;
+        const float *a0 = aff, *c0 = aff + DEC_H;
+#pragma unroll 1
+        for (int kp = 0; kp < DEC_KP; ++kp) {
+          const int col0 = kp * 64 + hsel * 32;
+          uint32_t v[32];
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float x0[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int col = col0 + j + u;
+              float acc = fmaf(px, s_wp[col], xb[col]);
+              acc = fmaf(py, s_wp[DEC_H + col], acc);
+              acc = fmaf(pz, s_wp[2 * DEC_H + col], acc);
+              x0[u] = acc;
+              v[j + u] = __float_as_uint(acc);
+            }
+            pk[j >> 1] = umma::pack_relu_bf16x2(fmaf(x0[0], a0[col0 + j], c0[col0 + j]),
+                                                fmaf(x0[1], a0[col0 + j + 1], c0[col0 + j + 1]));
+          }
+          umma::tmem_st32(tmem_x + lane_base + col0, v);
+          uint8_t *rowp = s_ah + kp * DEC_PANEL_A + r * 128;
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int cc = (hsel * 4 + c4) ^ (r & 7);
+            *reinterpret_cast<uint4 *>(rowp + (cc << 4)) = make_uint4(pk[c4 * 4], pk[c4 * 4 + 1], pk[c4 * 4 + 2], pk[c4 * 4 + 3]);
+          }
+          umma::tc_wait_st();
+          umma::fence_proxy_async_smem();
+          umma::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) umma::mbar_arrive(&bars->a_ready[kp]);
+        }
+      }
+      // ---- layers
+#pragma unroll 1
+      for (int l = 0; l < DEC_LAYERS; ++l, ++layer_count) {
+        umma::mbar_wait(&bars->acc_ready, layer_count & 1u);
+        umma::tc_fence_after();
+        const uint32_t src = ((l & 1) ? tmem_x : tmem_n) + lane_base;
+        const float *al = aff + (l + 1) * 2 * DEC_H, *cl = al + DEC_H;
+        if (l < DEC_LAYERS - 1) {
+#pragma unroll 1
+          for (int kp = 0; kp < DEC_KP; ++kp) {
+            const int col0 = kp * 64 + hsel * 32;
+            uint32_t v[32];
+            umma::tmem_ld32(src + col0, v);
+            umma::tc_wait_ld();
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 a4 = *reinterpret_cast<const float4 *>(al + col0 + j);
+              const float4 c4 = *reinterpret_cast<const float4 *>(cl + col0 + j);
+              pk[(j >> 1)] = umma::pack_relu_bf16x2(fmaf(__uint_as_float(v[j]), a4.x, c4.x),
+                                                    fmaf(__uint_as_float(v[j + 1]), a4.y, c4.y));
+              pk[(j >> 1) + 1] = umma::pack_relu_bf16x2(fmaf(__uint_as_float(v[j + 2]), a4.z, c4.z),
+                                                        fmaf(__uint_as_float(v[j + 3]), a4.w, c4.w));
+            }
+            uint8_t *rowp = s_ah + kp * DEC_PANEL_A + r * 128;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const int cc = (hsel * 4 + c4) ^ (r & 7);
+              *reinterpret_cast<uint4 *>(rowp + (cc << 4)) = make_uint4(pk[c4 * 4], pk[c4 * 4 + 1], pk[c4 * 4 + 2], pk[c4 * 4 + 3]);
+            }
+            umma::fence_proxy_async_smem();
+            umma::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&bars->a_ready[kp]);
+          }
+        } else {
+          // final: logits = fc_out(relu(cbn(x)))  -- fp32 dot product over the 256 channels
+          float part = 0.f;
+#pragma unroll 1
+          for (int kp = 0; kp < DEC_KP; ++kp) {
+            const int col0 = kp * 64 + hsel * 32;
+            uint32_t v[32];
+            umma::tmem_ld32(src + col0, v);
+            umma::tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float h = fmaxf(fmaf(__uint_as_float(v[j]), al[col0 + j], cl[col0 + j]), 0.f);
+              part = fmaf(h, s_wout[col0 + j], part);
+            }
+          }
+          s_out[hsel * DEC_TILE_M + r] = part;
+          umma::tc_fence_before();
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+          if (hsel == 0 && valid)
+            logits[(size_t)obj * T + t] = (s_out[r] + s_out[DEC_TILE_M + r]) + fc_out_b;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&bars->aff_empty[ab]);
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    umma::tc_fence_after();
+    umma::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: fc_w (10,256,256) f32 [layer][out n][in k]  ->  bf16, per (layer, k-panel) a 32-KB image of the
+// [256 rows n][64 k] K-major SWIZZLE_128B operand, stages in consumption order.
+__global__ void onet_pack_kernel(const float *__restrict__ fc_w, uint8_t *__restrict__ packed) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 8 consecutive k (16 bytes)
+  const int total = DEC_LAYERS * DEC_H * (DEC_H / 8);
+  if (e >= total) return;
+  const int l = e / (DEC_H * 32), rem = e % (DEC_H * 32);
+  const int n = rem / 32, kc = rem % 32;  // kc: 16-byte chunk index along k (0..31)
+  const int kp = kc / 8, cin = kc % 8;
+  const float *src = fc_w + ((size_t)l * DEC_H + n) * DEC_H + kc * 8;
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w[i] = umma::pack_bf16x2(src[2 * i], src[2 * i + 1]);
+  uint8_t *dst = packed + (size_t)(l * DEC_KP + kp) * DEC_STAGE_B + n * 128 + ((cin ^ (n & 7)) << 4);
+  *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// conditional-BN tables.  grid (11 layers, ceil(B/8)), 256 threads; each warp produces 32 channels for 8 objects.
+constexpr int CBN_OBJ = 8;
+__global__ void __launch_bounds__(256)
+onet_cbn_tables_kernel(const float *__restrict__ c, int B, int c_dim, const float *__restrict__ gamma_w,
+                       const float *__restrict__ gamma_b, const float *__restrict__ beta_w,
+                       const float *__restrict__ beta_b, const float *__restrict__ run_mean,
+                       const float *__restrict__ run_var, float eps, const float *__restrict__ fc_bias,
+                       const float *__restrict__ x_bias, float *__restrict__ aff) {
+  extern __shared__ float s_c[];  // [CBN_OBJ][c_dim]
+  const int l = blockIdx.x, b0 = blockIdx.y * CBN_OBJ;
+  const int nb = min(CBN_OBJ, B - b0);
+  for (int e = threadIdx.x; e < CBN_OBJ * c_dim; e += blockDim.x) {
+    const int o = e / c_dim, k = e % c_dim;
+    s_c[e] = o < nb ? __ldg(c + (size_t)(b0 + o) * c_dim + k) : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int ci = 0; ci < 32; ++ci) {
+    const int ch = warp * 32 + ci;
+    const float *gw = gamma_w + ((size_t)l * DEC_H + ch) * c_dim;
+    const float *bw = beta_w + ((size_t)l * DEC_H + ch) * c_dim;
+    float g[CBN_OBJ], bt[CBN_OBJ];
+#pragma unroll
+    for (int o = 0; o < CBN_OBJ; ++o) { g[o] = 0.f; bt[o] = 0.f; }
+    for (int k = lane; k < c_dim; k += 32) {
+      const float wg = __ldg(gw + k), wb = __ldg(bw + k);
+#pragma unroll
+      for (int o = 0; o < CBN_OBJ; ++o) {
+        const float cv = s_c[o * c_dim + k];
+        g[o] = fmaf(wg, cv, g[o]);
+        bt[o] = fmaf(wb, cv, bt[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < CBN_OBJ; ++o) {
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        g[o] += __shfl_xor_sync(0xffffffffu, g[o], off);
+        bt[o] += __shfl_xor_sync(0xffffffffu, bt[o], off);
+      }
+    }
+    if (lane < nb) {
+      float gam = 0.f, bet = 0.f;
+#pragma unroll
+      for (int o = 0; o < CBN_OBJ; ++o)
+        if (o == lane) { gam = g[o]; bet = bt[o]; }
+      gam += __ldg(gamma_b + l * DEC_H + ch);
+      bet += __ldg(beta_b + l * DEC_H + ch);
+      // bias still pending on the accumulator this CBN reads:
+      //   odd l  (bn_1 of block (l-1)/2): the bias of fc_0 = fc layer l-1
+      //   even l (bn_0 of block l/2, or the final bn): sum of the fc_1 biases of all previous blocks
+      float pend = 0.f;
+      if (l & 1) {
+        pend = __ldg(fc_bias + (l - 1) * DEC_H + ch);
+      } else {
+        for (int tblk = 0; tblk < l / 2; ++tblk) pend += __ldg(fc_bias + (2 * tblk + 1) * DEC_H + ch);
+      }
+      const float a = gam * rsqrtf(__ldg(run_var + l * DEC_H + ch) + eps);
+      const float cc = fmaf(a, pend - __ldg(run_mean + l * DEC_H + ch), bet);
+      float *rec = aff + (size_t)(b0 + lane) * DEC_AFF_FLOATS;
+      rec[l * 2 * DEC_H + ch] = a;
+      rec[l * 2 * DEC_H + DEC_H + ch] = cc;
+      if (l == 0) rec[DEC_CBN * 2 * DEC_H + ch] = __ldg(x_bias + (size_t)(b0 + lane) * DEC_H + ch);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 exact path pieces
+__global__ void dec_fcp_kernel(const float *__restrict__ p, long long p_stride, int T, const float *__restrict__ fc_p_w,
+                               const float *__restrict__ aff, int b0, float *__restrict__ x) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = blockIdx.y, bl = blockIdx.z;  // bl: object within chunk
+  if (t >= T) return;
+  const float *pp = p + (size_t)(b0 + bl) * p_stride + (size_t)t * 3;
+  const float xb = __ldg(aff + (size_t)(b0 + bl) * DEC_AFF_FLOATS + DEC_CBN * 2 * DEC_H + o);
+  float acc = fmaf(__ldg(pp), __ldg(fc_p_w + o * 3), xb);
+  acc = fmaf(__ldg(pp + 1), __ldg(fc_p_w + o * 3 + 1), acc);
+  acc = fmaf(__ldg(pp + 2), __ldg(fc_p_w + o * 3 + 2), acc);
+  x[((size_t)bl * DEC_H + o) * T + t] = acc;
+}
+
+__global__ void dec_out_kernel(const float *__restrict__ x, int T, const float *__restrict__ aff, int b0,
+                               const float *__restrict__ fc_out_w, float fc_out_b, float *__restrict__ logits) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int bl = blockIdx.y;
+  if (t >= T) return;
+  const float *rec = aff + (size_t)(b0 + bl) * DEC_AFF_FLOATS + 10 * 2 * DEC_H;
+  float acc = 0.f;
+  for (int k = 0; k < DEC_H; ++k) {
+    const float h = fmaxf(fmaf(__ldg(x + ((size_t)bl * DEC_H + k) * T + t), __ldg(rec + k), __ldg(rec + DEC_H + k)), 0.f);
+    acc = fmaf(h, __ldg(fc_out_w + k), acc);
+  }
+  logits[(size_t)(b0 + bl) * T + t] = acc + fc_out_b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 self-test: D (128x256 f32) = bf16(A (128x64)) . bf16(B (256x64))^T through exactly the descriptor,
+// swizzle, MMA, commit and TMEM-load helpers the decoder uses.
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ Bm, float *__restrict__ D) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *sa = smem, *sb = smem + DEC_PANEL_A;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_barrier_init(); }
+  if (warp == 0) umma::tmem_alloc(&tmem_ptr, 256);
+  for (int e = tid; e < 128 * 32; e += 128) {
+    const int row = e / 32, k2 = (e % 32) * 2;
+    *reinterpret_cast<uint32_t *>(sa + umma::sw128_offset(row, k2)) = umma::pack_bf16x2(A[row * 64 + k2], A[row * 64 + k2 + 1]);
+  }
+  for (int e = tid; e < 256 * 32; e += 128) {
+    const int row = e / 32, k2 = (e % 32) * 2;
+    *reinterpret_cast<uint32_t *>(sb + umma::sw128_offset(row, k2)) = umma::pack_bf16x2(Bm[row * 64 + k2], Bm[row * 64 + k2 + 1]);
+  }
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tb = tmem_ptr;
+  if (tid == 0) {
+    constexpr uint32_t idesc = umma::make_idesc_bf16_f32(128, 256);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma::mma_bf16_ss(tb, umma::make_desc_k_sw128(umma::smem_u32(sa) + k * 32),
+                        umma::make_desc_k_sw128(umma::smem_u32(sb) + k * 32), idesc, k != 0);
+    umma::mma_commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::tc_fence_after();
+  for (int c0 = 0; c0 < 256; c0 += 32) {
+    uint32_t v[32];
+    umma::tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + c0, v);
+    umma::tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) D[(warp * 32 + lane) * 256 + c0 + j] = __uint_as_float(v[j]);
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { umma::tc_fence_after(); umma::tmem_dealloc(tb, 256); }
+}
+
+}  // namespace rfd
+
+using namespace rfd;
+
+extern "C" size_t rfd_onet_packed_bytes(int nsplit) {
+  return nsplit == 1 ? (size_t)DEC_LAYERS * DEC_KP * DEC_STAGE_B : 0;
+}
+
+extern "C" size_t rfd_onet_aff_floats(void) { return DEC_AFF_FLOATS; }
+
+extern "C" int rfd_onet_pack_weights(const float *fc_w, int nsplit, void *packed, void *stream) {
+  if (!fc_w || !packed) return RFD_ERR_INVALID_ARGUMENT;
+  if (nsplit != 1) return RFD_ERR_UNSUPPORTED_SIZE;
+  const int total = DEC_LAYERS * DEC_H * (DEC_H / 8);
+  onet_pack_kernel<<<h_ceil_div(total, 256), 256, 0, as_stream(stream)>>>(fc_w, reinterpret_cast<uint8_t *>(packed));
+  RFD_CHECK_LAUNCH("onet_pack_kernel");
+  return RFD_OK;
+}
+
+extern "C" int rfd_onet_cbn_tables(const float *c, int B, int c_dim, const float *gamma_w, const float *gamma_b,
+                                   const float *beta_w, const float *beta_b, const float *run_mean,
+                                   const float *run_var, float eps, const float *fc_bias, const float *x_bias,
+                                   float *aff, void *stream) {
+  if (B < 0 || c_dim < 1) return RFD_ERR_INVALID_ARGUMENT;
+  if (B == 0) return RFD_OK;
+  if (!c || !gamma_w || !gamma_b || !beta_w || !beta_b || !run_mean || !run_var || !fc_bias || !x_bias || !aff)
+    return RFD_ERR_INVALID_ARGUMENT;
+  const size_t smem = sizeof(float) * CBN_OBJ * (size_t)c_dim;
+  if (smem > 96 * 1024 || h_ceil_div(B, CBN_OBJ) > 65535) return RFD_ERR_UNSUPPORTED_SIZE;
+  if (smem > 48 * 1024)
+    RFD_CHECK_CUDA(cudaFuncSetAttribute(onet_cbn_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                   "cbn attr");
+  dim3 grid(DEC_CBN, h_ceil_div(B, CBN_OBJ));
+  onet_cbn_tables_kernel<<<grid, 256, smem, as_stream(stream)>>>(c, B, c_dim, gamma_w, gamma_b, beta_w, beta_b, run_mean,
+                                                                  run_var, eps, fc_bias, x_bias, aff);
+  RFD_CHECK_LAUNCH("onet_cbn_tables_kernel");
+  return RFD_OK;
+}
+
+extern "C" int rfd_onet_decode(const float *p, long long p_batch_stride, int B, int T, const float *fc_p_w,
+                               const void *packed, int nsplit, const float *aff, const float *fc_out_w,
+                               float fc_out_b, float *logits, void *stream) {
+  if (B < 0 || T < 0 || p_batch_stride < 0) return RFD_ERR_INVALID_ARGUMENT;
+  if (B == 0 || T == 0) return RFD_OK;
+  if (!p || !fc_p_w || !packed || !aff || !fc_out_w || !logits) return RFD_ERR_INVALID_ARGUMENT;
+  if (nsplit != 1) return RFD_ERR_UNSUPPORTED_SIZE;
+  const long long tiles_per_obj = (T + DEC_TILE_M - 1) / DEC_TILE_M;
+  const long long num_tiles = tiles_per_obj * B;
+  if (num_tiles > 0x7fffffffLL) return RFD_ERR_UNSUPPORTED_SIZE;
+  int dev = 0, sms = 148;
+  RFD_CHECK_CUDA(cudaGetDevice(&dev), "decode getdevice");
+  RFD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "decode sms");
+  RFD_CHECK_CUDA(cudaFuncSetAttribute(onet_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES),
+                 "decode attr");
+  const int grid = (int)(num_tiles < sms ? num_tiles : sms);
+  onet_decode_kernel<<<grid, DEC_THREADS, DEC_SMEM_BYTES, as_stream(stream)>>>(
+      p, p_batch_stride, T, fc_p_w, reinterpret_cast<const uint8_t *>(packed), aff, fc_out_w, fc_out_b, logits,
+      (int)num_tiles, (int)tiles_per_obj);
+  RFD_CHECK_LAUNCH("onet_decode_kernel");
+  return RFD_OK;
+}
+
+extern "C" int rfd_onet_decode_f32(const float *p, long long p_batch_stride, int B, int T, const float *fc_p_w,
+                                   const float *fc_w, const float *aff, const float *fc_out_w, float fc_out_b,
+                                   float *logits, float *workspace, size_t workspace_bytes, void *stream) {
+  if (B < 0 || T < 0 || p_batch_stride < 0) return RFD_ERR_INVALID_ARGUMENT;
+  if (B == 0 || T == 0) return RFD_OK;
+  if (!p || !fc_p_w || !fc_w || !aff || !fc_out_w || !logits || !workspace) return RFD_ERR_INVALID_ARGUMENT;
+  const size_t per_obj = (size_t)2 * DEC_H * T * sizeof(float);
+  long long bc = (long long)(workspace_bytes / per_obj);
+  if (bc < 1) return RFD_ERR_INVALID_ARGUMENT;
+  if (bc > B) bc = B;
+  if (bc > 65535) bc = 65535;
+  cudaStream_t st = as_stream(stream);
+  static float *ones_zeros = nullptr;  // unit scale / zero shift for the bias-free layers
+  if (!ones_zeros) {
+    float h[2 * DEC_H];
+    for (int i = 0; i < DEC_H; ++i) { h[i] = 1.f; h[DEC_H + i] = 0.f; }
+    RFD_CHECK_CUDA(cudaMalloc(&ones_zeros, sizeof(h)), "decode_f32 malloc");
+    RFD_CHECK_CUDA(cudaMemcpy(ones_zeros, h, sizeof(h), cudaMemcpyHostToDevice), "decode_f32 memcpy");
+  }
+  for (int b0 = 0; b0 < B; b0 += (int)bc) {
+    const int nb = (int)((B - b0) < bc ? (B - b0) : bc);
+    float *x = workspace, *net = workspace + (size_t)bc * DEC_H * T;
+    dec_fcp_kernel<<<dim3(h_ceil_div(T, 256), DEC_H, nb), 256, 0, st>>>(p, p_batch_stride, T, fc_p_w, aff, b0, x);
+    RFD_CHECK_LAUNCH("dec_fcp_kernel");
+    const float *affb = aff + (size_t)b0 * DEC_AFF_FLOATS;
+    for (int i = 0; i < 5; ++i) {
+      // net = W_{2i} . relu(a_{2i} x + c_{2i})
+      int rc = launch_pointwise_f32(x, fc_w + (size_t)(2 * i) * DEC_H * DEC_H, ones_zeros, ones_zeros + DEC_H, nullptr,
+                                    affb + (2 * i) * 2 * DEC_H, affb + (2 * i) * 2 * DEC_H + DEC_H, DEC_AFF_FLOATS, 0, 1,
+                                    nb, DEC_H, DEC_H, T, net, st);
+      if (rc != RFD_OK) return rc;
+      // x = x + W_{2i+1} . relu(a_{2i+1} net + c_{2i+1})     (in place: each element read then written by one thread)
+      rc = launch_pointwise_f32(net, fc_w + (size_t)(2 * i + 1) * DEC_H * DEC_H, ones_zeros, ones_zeros + DEC_H, x,
+                                affb + (2 * i + 1) * 2 * DEC_H, affb + (2 * i + 1) * 2 * DEC_H + DEC_H, DEC_AFF_FLOATS,
+                                0, 1, nb, DEC_H, DEC_H, T, x, st);
+      if (rc != RFD_OK) return rc;
+    }
+    dec_out_kernel<<<dim3(h_ceil_div(T, 256), nb), 256, 0, st>>>(x, T, aff, b0, fc_out_w, fc_out_b, logits);
+    RFD_CHECK_LAUNCH("dec_out_kernel");
+  }
+  return RFD_OK;
+}
+
+extern "C" int rfd_umma_selftest(const float *A, const float *Bm, float *D, void *stream) {
+  if (!A || !Bm || !D) return RFD_ERR_INVALID_ARGUMENT;
+  const int smem = DEC_PANEL_A + DEC_STAGE_B + 1024;
+  RFD_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                 "selftest attr");
+  umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(A, Bm, D);
+  RFD_CHECK_LAUNCH("umma_selftest_kernel");
+  return RFD_OK;
+}

@@ -1,0 +1,66 @@
+"""Pointwise-MLP helpers: BatchNorm folding (eval mode) and launches of the fp32 layer kernel."""
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def fold_conv_bn(conv, bn=None):
+    """(W (Cout,Cin) f32, scale (Cout), shift (Cout)) with  bn(conv(x)) == scale * (W.x) + shift  in eval mode.
+
+    conv: nn.Conv1d / nn.Conv2d with kernel size 1 (or nn.Linear); bn: nn.BatchNorm{1,2}d or None."""
+    W = conv.weight.detach().reshape(conv.weight.shape[0], -1).float().contiguous()
+    cout = W.shape[0]
+    bias = conv.bias.detach().float() if conv.bias is not None else torch.zeros(cout, device=W.device)
+    if bn is None:
+        return W, torch.ones(cout, device=W.device), bias.contiguous()
+    inv = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+    g = bn.weight.detach().float() if bn.affine else torch.ones_like(inv)
+    b = bn.bias.detach().float() if bn.affine else torch.zeros_like(inv)
+    scale = g * inv
+    shift = b + (bias - bn.running_mean.detach().float()) * scale
+    return W, scale.contiguous(), shift.contiguous()
+
+
+def fold_sequential(seq):
+    """Fold an nn.Sequential of [Conv, (BN), (ReLU)]* (build_shared_mlp, pointnet2_modules.py:9-19)
+    into a list of (W, scale, shift, relu)."""
+    layers, mods, i = [], list(seq), 0
+    while i < len(mods):
+        conv = mods[i]
+        assert isinstance(conv, (nn.Conv1d, nn.Conv2d)), type(conv)
+        i += 1
+        bn = None
+        if i < len(mods) and isinstance(mods[i], (nn.BatchNorm1d, nn.BatchNorm2d)):
+            bn = mods[i]
+            i += 1
+        relu = False
+        if i < len(mods) and isinstance(mods[i], nn.ReLU):
+            relu = True
+            i += 1
+        W, s, t = fold_conv_bn(conv, bn)
+        layers.append((W, s, t, relu))
+    return layers
+
+
+def pointwise_layer(x, W, scale, shift, relu, pool=1, residual=None):
+    """y = act(scale * (W . x) + shift) (+ residual), optional max over runs of `pool` positions.
+    x (B,Cin,L) f32 contiguous CUDA -> (B,Cout,L//pool)."""
+    B, Cin, L = x.shape
+    Cout = W.shape[0]
+    assert W.shape[1] == Cin, (W.shape, Cin)
+    y = torch.empty((B, Cout, L // pool), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().rfd_pointwise_mlp_f32(
+            x.data_ptr(), W.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+            0 if residual is None else residual.data_ptr(), int(relu), int(pool), B, Cin, Cout, L, y.data_ptr(),
+            torch.cuda.current_stream().cuda_stream), "pointwise_mlp_f32")
+    return y
+
+
+def run_mlp(x, layers, pool_last=1):
+    """Apply folded layers to x (B,C,L); the last layer max-pools over runs of `pool_last`."""
+    for li, (W, s, t, relu) in enumerate(layers):
+        last = li == len(layers) - 1
+        x = pointwise_layer(x, W, s, t, relu, pool=pool_last if last else 1)
+    return x

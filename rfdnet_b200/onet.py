@@ -1,0 +1,222 @@
+"""Host-side mirror of the ONet occupancy decoder.
+
+Reference: models/iscnet/modules/occ_decoder.py:72-122 (DecoderCBatchNorm), layers.py:51-107
+(CResnetBlockConv1d), layers.py:193-242 (CBatchNorm1d), external/common.py:157-176 (make_3d_grid),
+generator.py:91-97,123-143 (dense 32^3 query, eval_points).
+
+`DecoderCBatchNorm` keeps the reference's parameter names / shapes (state_dict compatible:
+fc_p.weight (256,3,1), fc_z.weight (256,z), blocks.{i}.bn_{0,1}.conv_{gamma,beta}.weight (256,c,1),
+blocks.{i}.bn_{0,1}.bn.running_{mean,var}, blocks.{i}.fc_{0,1}.weight (256,256,1), bn.*, fc_out.weight (1,256,1)).
+forward(p, z, c) -> logits (B,T):
+  * eval mode, CUDA, no autograd: one persistent tcgen05 kernel (precision='bf16') or the fp32 CUDA-core
+    path (precision='fp32');
+  * otherwise (training / batch-statistics CBN): the reference's op sequence in PyTorch.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class CBatchNorm1d(nn.Module):
+    """layers.py:193-242"""
+
+    def __init__(self, c_dim, f_dim, norm_method='batch_norm'):
+        super().__init__()
+        assert norm_method == 'batch_norm'
+        self.c_dim, self.f_dim, self.norm_method = c_dim, f_dim, norm_method
+        self.conv_gamma = nn.Conv1d(c_dim, f_dim, 1)
+        self.conv_beta = nn.Conv1d(c_dim, f_dim, 1)
+        self.bn = nn.BatchNorm1d(f_dim, affine=False)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.zeros_(self.conv_gamma.weight)
+        nn.init.zeros_(self.conv_beta.weight)
+        nn.init.ones_(self.conv_gamma.bias)
+        nn.init.zeros_(self.conv_beta.bias)
+
+    def forward(self, x, c):
+        assert x.size(0) == c.size(0)
+        assert c.size(1) == self.c_dim
+        if len(c.size()) == 2:
+            c = c.unsqueeze(2)
+        gamma = self.conv_gamma(c)
+        beta = self.conv_beta(c)
+        net = self.bn(x)
+        return gamma * net + beta
+
+
+class CResnetBlockConv1d(nn.Module):
+    """layers.py:51-107 (size_in == size_h == size_out: no shortcut conv)"""
+
+    def __init__(self, c_dim, size_in, size_h=None, size_out=None, norm_method='batch_norm'):
+        super().__init__()
+        size_h = size_in if size_h is None else size_h
+        size_out = size_in if size_out is None else size_out
+        assert size_in == size_h == size_out, "the sm_100a decoder kernel is built for equal block widths"
+        self.size_in, self.size_h, self.size_out = size_in, size_h, size_out
+        self.bn_0 = CBatchNorm1d(c_dim, size_in, norm_method=norm_method)
+        self.bn_1 = CBatchNorm1d(c_dim, size_h, norm_method=norm_method)
+        self.fc_0 = nn.Conv1d(size_in, size_h, 1)
+        self.fc_1 = nn.Conv1d(size_h, size_out, 1)
+        self.actvn = nn.ReLU()
+        self.shortcut = None
+        nn.init.zeros_(self.fc_1.weight)
+
+    def forward(self, x, c):
+        net = self.fc_0(self.actvn(self.bn_0(x, c)))
+        dx = self.fc_1(self.actvn(self.bn_1(net, c)))
+        return x + dx
+
+
+class DecoderCBatchNorm(nn.Module):
+    """occ_decoder.py:72-122"""
+
+    def __init__(self, dim=3, z_dim=128, c_dim=128, hidden_size=256, n_blocks=5, leaky=False, legacy=False,
+                 precision='bf16'):
+        super().__init__()
+        assert not leaky and not legacy
+        self.z_dim, self.c_dim, self.hidden_size, self.n_blocks = z_dim, c_dim, hidden_size, n_blocks
+        if not z_dim == 0:
+            self.fc_z = nn.Linear(z_dim, hidden_size)
+        self.fc_p = nn.Conv1d(dim, hidden_size, 1)
+        self.blocks = nn.ModuleList([CResnetBlockConv1d(c_dim, hidden_size) for _ in range(n_blocks)])
+        self.bn = CBatchNorm1d(c_dim, hidden_size)
+        self.fc_out = nn.Conv1d(hidden_size, 1, 1)
+        self.actvn = nn.ReLU()
+        self.precision = precision
+        self._packed = None
+
+    # -- cache invalidation
+    def train(self, mode=True):
+        self._packed = None
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def _cbn_layers(self):
+        out = []
+        for blk in self.blocks:
+            out += [blk.bn_0, blk.bn_1]
+        return out + [self.bn]
+
+    def _fc_layers(self):
+        out = []
+        for blk in self.blocks:
+            out += [blk.fc_0, blk.fc_1]
+        return out
+
+    def pack(self):
+        """Gather the parameters into the flat device arrays the C ABI takes (cached until the weights change)."""
+        if self._packed is not None:
+            return self._packed
+        assert self.hidden_size == 256 and self.n_blocks == 5, "kernel is built for hidden 256, 5 blocks"
+        lib = _lib.load()
+        cbn, fcs = self._cbn_layers(), self._fc_layers()
+        dev = self.fc_p.weight.device
+        f32 = lambda t: t.detach().float().contiguous()
+        P = {
+            'fc_w': torch.stack([f32(l.weight).view(256, 256) for l in fcs]).contiguous(),
+            'fc_b': torch.stack([f32(l.bias) for l in fcs]).contiguous(),
+            'gamma_w': torch.stack([f32(l.conv_gamma.weight).view(256, self.c_dim) for l in cbn]).contiguous(),
+            'gamma_b': torch.stack([f32(l.conv_gamma.bias) for l in cbn]).contiguous(),
+            'beta_w': torch.stack([f32(l.conv_beta.weight).view(256, self.c_dim) for l in cbn]).contiguous(),
+            'beta_b': torch.stack([f32(l.conv_beta.bias) for l in cbn]).contiguous(),
+            'mean': torch.stack([f32(l.bn.running_mean) for l in cbn]).contiguous(),
+            'var': torch.stack([f32(l.bn.running_var) for l in cbn]).contiguous(),
+            'eps': float(cbn[0].bn.eps),
+            'fc_p_w': f32(self.fc_p.weight).view(256, 3).contiguous(),
+            'fc_out_w': f32(self.fc_out.weight).view(256).contiguous(),
+            'fc_out_b': float(self.fc_out.bias.detach().float().item()),
+        }
+        nbytes = lib.rfd_onet_packed_bytes(1)
+        P['packed'] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.rfd_onet_pack_weights(P['fc_w'].data_ptr(), 1, P['packed'].data_ptr(),
+                                                 torch.cuda.current_stream().cuda_stream), "onet_pack_weights")
+        self._packed = P
+        return P
+
+    def cbn_tables(self, z, c):
+        """(B, aff_floats) per-object affine tables + x_bias (rfd_onet_cbn_tables)."""
+        P = self.pack()
+        lib = _lib.load()
+        B = c.shape[0]
+        x_bias = self.fc_p.bias.detach().float().unsqueeze(0).expand(B, -1)
+        if self.z_dim != 0:
+            x_bias = x_bias + torch.nn.functional.linear(z.float(), self.fc_z.weight.detach().float(),
+                                                         self.fc_z.bias.detach().float())
+        x_bias = x_bias.contiguous()
+        c = c.detach().float().contiguous()
+        aff = torch.empty((B, lib.rfd_onet_aff_floats()), dtype=torch.float32, device=c.device)
+        with torch.cuda.device(c.device):
+            _lib.check(lib.rfd_onet_cbn_tables(
+                c.data_ptr(), B, self.c_dim, P['gamma_w'].data_ptr(), P['gamma_b'].data_ptr(),
+                P['beta_w'].data_ptr(), P['beta_b'].data_ptr(), P['mean'].data_ptr(), P['var'].data_ptr(), P['eps'],
+                P['fc_b'].data_ptr(), x_bias.data_ptr(), aff.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                "onet_cbn_tables")
+        return aff
+
+    def decode(self, p, z, c, precision=None, workspace_bytes=1 << 30):
+        """p: (B,T,3) or a shared (T,3) lattice; returns logits (B,T) f32."""
+        precision = precision or self.precision
+        P = self.pack()
+        lib = _lib.load()
+        B = c.shape[0]
+        p = p.detach().float().contiguous()
+        if p.dim() == 2:
+            T, stride = p.shape[0], 0
+        else:
+            assert p.shape[0] == B
+            T, stride = p.shape[1], p.shape[1] * 3
+        aff = self.cbn_tables(z, c)
+        logits = torch.empty((B, T), dtype=torch.float32, device=c.device)
+        with torch.cuda.device(c.device):
+            st = torch.cuda.current_stream().cuda_stream
+            if precision == 'bf16':
+                _lib.check(lib.rfd_onet_decode(p.data_ptr(), stride, B, T, P['fc_p_w'].data_ptr(),
+                                               P['packed'].data_ptr(), 1, aff.data_ptr(), P['fc_out_w'].data_ptr(),
+                                               P['fc_out_b'], logits.data_ptr(), st), "onet_decode")
+            elif precision == 'fp32':
+                per_obj = 2 * 256 * T * 4
+                nobj = max(1, min(B, workspace_bytes // per_obj))
+                ws = torch.empty(nobj * per_obj // 4, dtype=torch.float32, device=c.device)
+                _lib.check(lib.rfd_onet_decode_f32(p.data_ptr(), stride, B, T, P['fc_p_w'].data_ptr(),
+                                                   P['fc_w'].data_ptr(), aff.data_ptr(), P['fc_out_w'].data_ptr(),
+                                                   P['fc_out_b'], logits.data_ptr(), ws.data_ptr(), ws.numel() * 4,
+                                                   st), "onet_decode_f32")
+            else:
+                raise ValueError(precision)
+        return logits
+
+    def forward(self, p, z, c, **kwargs):
+        fast = (not self.training and not torch.is_grad_enabled() and p.is_cuda
+                and self.hidden_size == 256 and self.n_blocks == 5)
+        if fast:
+            return self.decode(p, z, c)
+        # reference sequence, occ_decoder.py:110-122
+        p = p.transpose(1, 2)
+        net = self.fc_p(p)
+        if self.z_dim != 0:
+            net = net + self.fc_z(z).unsqueeze(2)
+        for block in self.blocks:
+            net = block(net, c)
+        out = self.fc_out(self.actvn(self.bn(net, c)))
+        return out.squeeze(1)
+
+
+def make_3d_grid(resolution=32, box_size=1.1, device='cuda'):
+    """box_size * make_3d_grid((-0.5,)*3, (0.5,)*3, (R,)*3) (external/common.py:157-176; generator.py:92-95),
+    generated on the device."""
+    out = torch.empty((resolution ** 3, 3), dtype=torch.float32, device=device)
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.load().rfd_make_3d_grid(int(resolution), float(box_size), out.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), "make_3d_grid")
+    return out

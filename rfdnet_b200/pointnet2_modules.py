@@ -1,0 +1,171 @@
+"""Host-side mirror of the reference SA / FP modules
+(external/pointnet2_ops_lib/pointnet2_ops/pointnet2_modules.py: build_shared_mlp :9-19,
+PointnetSAModuleVotes :149-260, PointnetFPModule :345-405).
+
+Same constructor arguments, forward signatures, return values and state_dict keys
+(`mlp_module.{0,3,6}.weight`, `mlp_module.{1,4,7}.*`, `mlp.*`), so reference checkpoints load.
+In eval mode without autograd the forward runs entirely on the sm_100a kernels
+(FPS -> fused ball-query+group -> folded-BN MLP + max); with autograd enabled (training,
+config 5) the reference's op sequence runs on the drop-in `_ext` kernels + torch autograd.
+"""
+from typing import List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, mlp as _mlp, pointnet2_utils
+
+
+def build_shared_mlp(mlp_spec: List[int], bn: bool = True):
+    layers = []
+    for i in range(1, len(mlp_spec)):
+        layers.append(nn.Conv2d(mlp_spec[i - 1], mlp_spec[i], kernel_size=1, bias=not bn))
+        if bn:
+            layers.append(nn.BatchNorm2d(mlp_spec[i]))
+        layers.append(nn.ReLU(True))
+    return nn.Sequential(*layers)
+
+
+class _FoldCache:
+    """Lazily folded (W, scale, shift, relu) per layer; dropped on train() / load_state_dict()."""
+
+    def _folded(self, seq):
+        if getattr(self, "_fold", None) is None:
+            self._fold = _mlp.fold_sequential(seq)
+        return self._fold
+
+    def train(self, mode=True):
+        self._fold = None
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._fold = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._fold = None
+        return super()._apply(fn, *a, **k)
+
+
+class PointnetSAModuleVotes(_FoldCache, nn.Module):
+    """pointnet2_modules.py:149-260 (pooling 'max' | 'avg' | 'rbf')."""
+
+    def __init__(self, *, mlp: List[int], npoint: int = None, radius: float = None, nsample: int = None,
+                 bn: bool = True, use_xyz: bool = True, pooling: str = 'max', sigma: float = None,
+                 normalize_xyz: bool = False, sample_uniformly: bool = False, ret_unique_cnt: bool = False):
+        super().__init__()
+        self.npoint, self.radius, self.nsample = npoint, radius, nsample
+        self.pooling = pooling
+        self.use_xyz = use_xyz
+        self.sigma = sigma if sigma is not None else (self.radius / 2 if self.radius is not None else None)
+        self.normalize_xyz = normalize_xyz
+        self.ret_unique_cnt = ret_unique_cnt
+        self.sample_uniformly = sample_uniformly
+        if npoint is not None:
+            self.grouper = pointnet2_utils.QueryAndGroup(radius, nsample, use_xyz=use_xyz, ret_grouped_xyz=True,
+                                                         normalize_xyz=normalize_xyz,
+                                                         sample_uniformly=sample_uniformly,
+                                                         ret_unique_cnt=ret_unique_cnt)
+        else:
+            self.grouper = pointnet2_utils.GroupAll(use_xyz, ret_grouped_xyz=True)
+        mlp_spec = list(mlp)
+        if use_xyz and len(mlp_spec) > 0:
+            mlp_spec[0] += 3
+        self.mlp_module = build_shared_mlp(mlp_spec, bn=bn)
+        self._fold = None
+
+    def _fast_ok(self, xyz, features):
+        return (not self.training and not torch.is_grad_enabled() and self.npoint is not None
+                and self.pooling == 'max' and not self.sample_uniformly and xyz.is_cuda
+                and self.nsample in (4, 8, 16, 32, 64))
+
+    def forward(self, xyz, features=None, inds=None):
+        if self._fast_ok(xyz, features):
+            return self._forward_fused(xyz, features, inds)
+        return self._forward_reference(xyz, features, inds)
+
+    # -- inference: sm_100a kernels end to end
+    def _forward_fused(self, xyz, features, inds):
+        xyz = xyz.contiguous()
+        B, N, _ = xyz.shape
+        if inds is None:
+            inds = pointnet2_utils._ext.furthest_point_sampling(xyz, self.npoint)
+        else:
+            assert inds.shape[1] == self.npoint
+        new_xyz = torch.gather(xyz, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3))  # exact copy of rows
+        grouped, _, _ = pointnet2_utils.fused_query_and_group(
+            xyz, new_xyz, None if features is None else features.contiguous(), self.radius, self.nsample,
+            self.use_xyz, self.normalize_xyz)
+        Ct = grouped.shape[1]
+        x = grouped.view(B, Ct, self.npoint * self.nsample)
+        new_features = _mlp.run_mlp(x, self._folded(self.mlp_module), pool_last=self.nsample)
+        return new_xyz, new_features, inds
+
+    # -- training / generic: the reference's sequence (:219-260) on the drop-in ops
+    def _forward_reference(self, xyz, features, inds):
+        xyz_flipped = xyz.transpose(1, 2).contiguous()
+        if inds is None:
+            inds = pointnet2_utils.furthest_point_sample(xyz, self.npoint) if self.npoint is not None else None
+        else:
+            assert inds.shape[1] == self.npoint
+        new_xyz = pointnet2_utils.gather_operation(xyz_flipped, inds).transpose(1, 2).contiguous() \
+            if self.npoint is not None else None
+        if not self.ret_unique_cnt:
+            grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
+        else:
+            grouped_features, grouped_xyz, unique_cnt = self.grouper(xyz, new_xyz, features)
+        new_features = self.mlp_module(grouped_features)
+        if self.pooling == 'max':
+            new_features = F.max_pool2d(new_features, kernel_size=[1, new_features.size(3)])
+        elif self.pooling == 'avg':
+            new_features = F.avg_pool2d(new_features, kernel_size=[1, new_features.size(3)])
+        elif self.pooling == 'rbf':
+            rbf = torch.exp(-1 * grouped_xyz.pow(2).sum(1, keepdim=False) / (self.sigma ** 2) / 2)
+            new_features = torch.sum(new_features * rbf.unsqueeze(1), -1, keepdim=True) / float(self.nsample)
+        new_features = new_features.squeeze(-1)
+        if not self.ret_unique_cnt:
+            return new_xyz, new_features, inds
+        return new_xyz, new_features, inds, unique_cnt
+
+
+class PointnetFPModule(_FoldCache, nn.Module):
+    """pointnet2_modules.py:345-405."""
+
+    def __init__(self, mlp, bn=True):
+        super().__init__()
+        self.mlp = build_shared_mlp(list(mlp), bn=bn)
+        self._fold = None
+
+    def forward(self, unknown, known, unknow_feats, known_feats):
+        fast = (not self.training and not torch.is_grad_enabled() and known is not None and unknown.is_cuda)
+        if fast:
+            unknown, known = unknown.contiguous(), known.contiguous()
+            known_feats = known_feats.contiguous()
+            B, n, _ = unknown.shape
+            m = known.shape[1]
+            C2 = known_feats.shape[1]
+            C1 = 0 if unknow_feats is None else unknow_feats.shape[1]
+            x = torch.empty((B, C2 + C1, n), dtype=torch.float32, device=unknown.device)
+            with torch.cuda.device(unknown.device):
+                _lib.check(_lib.load().rfd_three_nn_interpolate(
+                    unknown.data_ptr(), known.data_ptr(), known_feats.data_ptr(), B, n, m, C2, C2 + C1,
+                    x.data_ptr(), torch.cuda.current_stream().cuda_stream), "three_nn_interpolate")
+            if C1:
+                x[:, C2:, :] = unknow_feats
+            return _mlp.run_mlp(x, self._folded(self.mlp))
+        if known is not None:
+            dist, idx = pointnet2_utils.three_nn(unknown, known)
+            dist_recip = 1.0 / (dist + 1e-8)
+            norm = torch.sum(dist_recip, dim=2, keepdim=True)
+            weight = dist_recip / norm
+            interpolated_feats = pointnet2_utils.three_interpolate(known_feats, idx, weight)
+        else:
+            interpolated_feats = known_feats.expand(*(list(known_feats.size()[0:2]) + [unknown.size(1)]))
+        if unknow_feats is not None:
+            new_features = torch.cat([interpolated_feats, unknow_feats], dim=1)
+        else:
+            new_features = interpolated_feats
+        new_features = new_features.unsqueeze(-1)
+        new_features = self.mlp(new_features)
+        return new_features.squeeze(-1)

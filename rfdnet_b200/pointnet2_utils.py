@@ -1,0 +1,210 @@
+"""Host-side mirror of the reference's `pointnet2_ops.pointnet2_utils`
+(external/pointnet2_ops_lib/pointnet2_ops/pointnet2_utils.py:34-411): the same autograd
+Functions and grouper modules, same names / argument order / return types, running on
+rfdnet_b200._ext (hand-written sm_100a kernels behind the C ABI)."""
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import _ext, _lib
+
+
+class FurthestPointSampling(Function):
+    """pointnet2_utils.py:34-65"""
+
+    @staticmethod
+    def forward(ctx, xyz, npoint):
+        out = _ext.furthest_point_sampling(xyz, npoint)
+        ctx.mark_non_differentiable(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return ()
+
+
+furthest_point_sample = FurthestPointSampling.apply
+
+
+class GatherOperation(Function):
+    """pointnet2_utils.py:68-101"""
+
+    @staticmethod
+    def forward(ctx, features, idx):
+        ctx.save_for_backward(idx, features)
+        return _ext.gather_points(features, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, features = ctx.saved_tensors
+        N = features.size(2)
+        return _ext.gather_points_grad(grad_out.contiguous(), idx, N), None
+
+
+gather_operation = GatherOperation.apply
+
+
+class ThreeNN(Function):
+    """pointnet2_utils.py:104-136 (returns sqrt of the squared distances, :125)"""
+
+    @staticmethod
+    def forward(ctx, unknown, known):
+        dist2, idx = _ext.three_nn(unknown, known)
+        dist = torch.sqrt(dist2)
+        ctx.mark_non_differentiable(dist, idx)
+        return dist, idx
+
+    @staticmethod
+    def backward(ctx, grad_dist, grad_idx):
+        return ()
+
+
+three_nn = ThreeNN.apply
+
+
+class ThreeInterpolate(Function):
+    """pointnet2_utils.py:139-191"""
+
+    @staticmethod
+    def forward(ctx, features, idx, weight):
+        ctx.save_for_backward(idx, weight, features)
+        return _ext.three_interpolate(features, idx, weight)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, weight, features = ctx.saved_tensors
+        m = features.size(2)
+        grad_features = _ext.three_interpolate_grad(grad_out.contiguous(), idx, weight, m)
+        return grad_features, torch.zeros_like(idx), torch.zeros_like(weight)
+
+
+three_interpolate = ThreeInterpolate.apply
+
+
+class GroupingOperation(Function):
+    """pointnet2_utils.py:194-240"""
+
+    @staticmethod
+    def forward(ctx, features, idx):
+        ctx.save_for_backward(idx, features)
+        return _ext.group_points(features, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, features = ctx.saved_tensors
+        N = features.size(2)
+        return _ext.group_points_grad(grad_out.contiguous(), idx, N), torch.zeros_like(idx)
+
+
+grouping_operation = GroupingOperation.apply
+
+
+class BallQuery(Function):
+    """pointnet2_utils.py:243-276 -- note the Python-side order (radius, nsample, xyz, new_xyz)."""
+
+    @staticmethod
+    def forward(ctx, radius, nsample, xyz, new_xyz):
+        output = _ext.ball_query(new_xyz, xyz, radius, nsample)
+        ctx.mark_non_differentiable(output)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return ()
+
+
+ball_query = BallQuery.apply
+
+
+def fused_query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz=True, normalize_xyz=False,
+                          ret_grouped_xyz=False, ret_idx=False):
+    """One kernel for QueryAndGroup.forward (pointnet2_utils.py:319-344): ball query + both gathers +
+    centring + radius normalisation + concatenation.  Inference path (no autograd graph)."""
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    C = 0 if features is None else features.shape[1]
+    Ct = (3 if use_xyz else 0) + C
+    dev = xyz.device
+    out = torch.empty((B, Ct, M, nsample), dtype=torch.float32, device=dev)
+    gxyz = torch.empty((B, 3, M, nsample), dtype=torch.float32, device=dev) if ret_grouped_xyz else None
+    idx = torch.empty((B, M, nsample), dtype=torch.int32, device=dev) if ret_idx else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().rfd_query_and_group(
+            xyz.data_ptr(), new_xyz.data_ptr(), 0 if features is None else features.data_ptr(), B, N, M, C,
+            float(radius), int(nsample), int(bool(use_xyz)), int(bool(normalize_xyz)), out.data_ptr(),
+            0 if gxyz is None else gxyz.data_ptr(), 0 if idx is None else idx.data_ptr(),
+            torch.cuda.current_stream().cuda_stream), "query_and_group")
+    return out, gxyz, idx
+
+
+class QueryAndGroup(nn.Module):
+    """pointnet2_utils.py:279-361.  Under autograd (training) the reference's op sequence runs on the
+    drop-in kernels so gradients flow exactly as in the reference; without grad the fused kernel is used."""
+
+    def __init__(self, radius, nsample, use_xyz=True, ret_grouped_xyz=False, normalize_xyz=False,
+                 sample_uniformly=False, ret_unique_cnt=False):
+        super().__init__()
+        self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
+        self.ret_grouped_xyz = ret_grouped_xyz
+        self.normalize_xyz = normalize_xyz
+        self.sample_uniformly = sample_uniformly
+        self.ret_unique_cnt = ret_unique_cnt
+        if self.ret_unique_cnt:
+            assert self.sample_uniformly
+
+    def forward(self, xyz, new_xyz, features=None):
+        needs_grad = torch.is_grad_enabled() and (
+            xyz.requires_grad or new_xyz.requires_grad or (features is not None and features.requires_grad))
+        if features is None:
+            assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
+        if not needs_grad and not self.sample_uniformly and self.nsample <= 128:
+            new_features, grouped_xyz, _ = fused_query_and_group(
+                xyz.contiguous(), new_xyz.contiguous(), None if features is None else features.contiguous(),
+                self.radius, self.nsample, self.use_xyz, self.normalize_xyz, ret_grouped_xyz=self.ret_grouped_xyz)
+            return (new_features, grouped_xyz) if self.ret_grouped_xyz else new_features
+
+        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        if self.sample_uniformly:  # pointnet2_utils.py:321-330 (host loop, kept for API completeness)
+            unique_cnt = torch.zeros((idx.shape[0], idx.shape[1]))
+            for i_batch in range(idx.shape[0]):
+                for i_region in range(idx.shape[1]):
+                    unique_ind = torch.unique(idx[i_batch, i_region, :])
+                    num_unique = unique_ind.shape[0]
+                    unique_cnt[i_batch, i_region] = num_unique
+                    sample_ind = torch.randint(0, num_unique, (self.nsample - num_unique,), dtype=torch.long)
+                    all_ind = torch.cat((unique_ind, unique_ind[sample_ind]))
+                    idx[i_batch, i_region, :] = all_ind
+        xyz_trans = xyz.transpose(1, 2).contiguous()
+        grouped_xyz = grouping_operation(xyz_trans, idx)
+        grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
+        if self.normalize_xyz:
+            grouped_xyz = grouped_xyz / self.radius
+        if features is not None:
+            grouped_features = grouping_operation(features, idx)
+            new_features = torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz else grouped_features
+        else:
+            new_features = grouped_xyz
+        ret = [new_features]
+        if self.ret_grouped_xyz:
+            ret.append(grouped_xyz)
+        if self.ret_unique_cnt:
+            ret.append(unique_cnt)
+        return ret[0] if len(ret) == 1 else tuple(ret)
+
+
+class GroupAll(nn.Module):
+    """pointnet2_utils.py:364-411"""
+
+    def __init__(self, use_xyz=True, ret_grouped_xyz=False):
+        super().__init__()
+        self.use_xyz = use_xyz
+        self.ret_grouped_xyz = ret_grouped_xyz
+
+    def forward(self, xyz, new_xyz, features=None):
+        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
+        if features is not None:
+            grouped_features = features.unsqueeze(2)
+            new_features = torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz else grouped_features
+        else:
+            new_features = grouped_xyz
+        return (new_features, grouped_xyz) if self.ret_grouped_xyz else new_features
