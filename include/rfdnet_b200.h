@@ -122,7 +122,8 @@ int rfd_make_3d_grid(int R, float box_size, float *out, void *stream);
  *   fc_bias (10,256) biases of the fc layers above; x_bias (B,256) = fc_p.bias + fc_z(z) (+ fc_z.bias)
  *   -> aff (B, rfd_onet_aff_floats()) f32: per object [11][2][256] scale a / shift c with
  *      relu(CBN_l(x_true)) == relu(a * x_acc + c)  (x_acc = bias-free accumulator held by the kernel),
- *      followed by the 256 x_bias values.
+ *      the 256 x_bias values, and the same (a,c) again in the column-pair-interleaved order
+ *      [11][128]{a0,a1,c0,c1} the tensor-core kernel stages in shared memory.
  * Step 3: logits (B,T) = decoder(p).  p is (B,T,3) with p_batch_stride = T*3 floats, or one shared
  *   (T,3) lattice for every object with p_batch_stride = 0.
  * nsplit = 1: bf16 operands, fp32 accumulation/residual (config 4).  nsplit = 3 (bf16x3) is reserved:

@@ -72,3 +72,29 @@ def check(status, what):
 
 def launch_count():
     return int(load().rfd_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------------
+# optional per-call device timing (bench.py): CUDA events recorded on the launching stream around a call.
+TIMERS = None  # None = off; list = collect (name, start_event, end_event, work) tuples
+
+
+class timed:
+    """`with timed("name", work): launch(...)` -- no-op unless TIMERS is a list.  Never synchronises."""
+
+    def __init__(self, name, work=0.0):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if TIMERS is not None:
+            import torch
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if TIMERS is not None:
+            self.e.record()
+            TIMERS.append((self.name, self.s, self.e, self.work))
+        return False

@@ -37,8 +37,15 @@ constexpr int DEC_KP = 4;
 constexpr int DEC_PANEL_A = DEC_TILE_M * 128;   // 16384 B : 128 rows x 64 bf16
 constexpr int DEC_STAGE_B = DEC_H * 128;        // 32768 B : 256 rows x 64 bf16
 constexpr int DEC_NSTAGE = 3;
-constexpr int DEC_AFF_FLOATS = DEC_CBN * 2 * DEC_H + DEC_H;  // 5888 floats / object (a,c per layer + x_bias)
+// per-object record in global memory (rfd_onet_cbn_tables):
+//   [0, 5632)      plain   [11 layers][a: 256][c: 256]                      (fp32 path)
+//   [5632, 5888)   x_bias  [256]
+//   [5888, 11520)  paired  [11 layers][128 column pairs]{a0, a1, c0, c1}    (tensor-core path)
+// the tensor-core kernel bulk-copies [5632, 11520) = DEC_AFF_FLOATS floats per tile.
+constexpr int DEC_PLAIN_FLOATS = DEC_CBN * 2 * DEC_H;         // 5632
+constexpr int DEC_AFF_FLOATS = DEC_H + DEC_CBN * 2 * DEC_H;   // 5888 floats staged in shared memory
 constexpr int DEC_AFF_BYTES = DEC_AFF_FLOATS * 4;             // 23552
+constexpr int DEC_REC_FLOATS = DEC_PLAIN_FLOATS + DEC_AFF_FLOATS;  // 11520
 constexpr int DEC_THREADS = 320;                // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
 constexpr int DEC_EPI_WARPS = 8;
 
@@ -107,7 +114,7 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         if (it == 0) {
           umma::mbar_arrive_expect_tx(&bars->aff_full[0], DEC_AFF_BYTES);
-          umma::bulk_g2s(s_aff, aff_all + (size_t)(tile / tiles_per_obj) * DEC_AFF_FLOATS, DEC_AFF_BYTES,
+          umma::bulk_g2s(s_aff, aff_all + (size_t)(tile / tiles_per_obj) * DEC_REC_FLOATS + DEC_PLAIN_FLOATS, DEC_AFF_BYTES,
                          &bars->aff_full[0]);
         }
         for (int s = 0; s < DEC_LAYERS * DEC_KP; ++s) {
@@ -118,8 +125,9 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
               const uint32_t n = (uint32_t)(it + 1) >> 1;  // use count of that buffer
               umma::mbar_wait(&bars->aff_empty[nb], (n & 1u) ^ 1u);
               umma::mbar_arrive_expect_tx(&bars->aff_full[nb], DEC_AFF_BYTES);
-              umma::bulk_g2s(s_aff + nb * DEC_AFF_FLOATS, aff_all + (size_t)(next / tiles_per_obj) * DEC_AFF_FLOATS,
-                             DEC_AFF_BYTES, &bars->aff_full[nb]);
+              umma::bulk_g2s(s_aff + nb * DEC_AFF_FLOATS,
+                             aff_all + (size_t)(next / tiles_per_obj) * DEC_REC_FLOATS + DEC_PLAIN_FLOATS, DEC_AFF_BYTES,
+                             &bars->aff_full[nb]);
             }
           }
           umma::mbar_wait(&bars->w_empty[st], ph ^ 1u);
@@ -157,56 +165,62 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
     }
   } else {
     // ===================== epilogue warps (8): TMEM -> affine+ReLU -> bf16 A panels =====================
+    // TMEM is read with the 16x256b shape: a thread then owns 4 ROWS x (2 adjacent columns per 8-column block), so
+    // one per-channel (a,c) fetch from shared memory serves four rows and every shared-memory store of a warp is a
+    // conflict-free 128-byte wavefront (8 rows x 16 B after the 128B swizzle).
     const int ew = warp - 2;
     const int q = warp & 3;     // TMEM lane quarter this warp may access
     const int hsel = ew >> 2;   // which 32-column half of every 64-column panel
-    const int r = q * 32 + lane;  // row of the tile owned by this thread
+    const int lr = lane >> 2;   // 0..7  row within an 8-row group  (== row & 7 : the swizzle phase)
+    const int lc = lane & 3;    // 0..3  column pair within an 8-column block
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint32_t layer_count = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int obj = tile / tiles_per_obj;
-      const int t = (tile - obj * tiles_per_obj) * DEC_TILE_M + r;
-      const bool valid = t < T;
+      const int t0 = (tile - obj * tiles_per_obj) * DEC_TILE_M + q * 32 + lr;  // row j of this thread: t0 + 8j
       const int ab = it & 1;
       umma::mbar_wait(&bars->aff_full[ab], ((uint32_t)it >> 1) & 1u);
-      const float *aff = s_aff + ab * DEC_AFF_FLOATS;
-      float px = 0.f, py = 0.f, pz = 0.f;
-      if (valid) {
-        const float *pp = p + (size_t)obj * p_stride + (size_t)t * 3;
-        px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
-      }
+      const float *aff = s_aff + ab * DEC_AFF_FLOATS;   // [x_bias 256][11 layers][128 column pairs]{a0,a1,c0,c1}
+      const float4 *affi = reinterpret_cast<const float4 *>(aff + DEC_H);
       // ---- E0: x0 = fc_p(p) + (fc_p.bias + fc_z(z)) in fp32 -> TMEM ; h0 = relu(a0*x0 + c0) -> A panels
       {
-        const float *xb = aff + DEC_CBN * 2 * DEC_H;
-        const float *a0 = aff, *c0 = aff + DEC_H;
+        float px[4], py[4], pz[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int t = t0 + 8 * j;
+          px[j] = py[j] = pz[j] = 0.f;
+          if (t < T) {
+            const float *pp = p + (size_t)obj * p_stride + (size_t)t * 3;
+            px[j] = __ldg(pp); py[j] = __ldg(pp + 1); pz[j] = __ldg(pp + 2);
+          }
+        }
 #pragma unroll 1
         for (int kp = 0; kp < DEC_KP; ++kp) {
-          const int col0 = kp * 64 + hsel * 32;
-          uint32_t v[32];
-          uint32_t pk[16];
+          const int cb = kp * 64 + hsel * 32;
+          uint32_t v[2][16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float x0[2];
+          for (int i = 0; i < 4; ++i) {
+            const int col = cb + 8 * i + 2 * lc;
+            const float2 w0 = *reinterpret_cast<const float2 *>(s_wp + col);
+            const float2 w1 = *reinterpret_cast<const float2 *>(s_wp + DEC_H + col);
+            const float2 w2 = *reinterpret_cast<const float2 *>(s_wp + 2 * DEC_H + col);
+            const float2 xb = *reinterpret_cast<const float2 *>(aff + col);
+            const float4 ac = affi[col >> 1];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int col = col0 + j + u;
-              float acc = fmaf(px, s_wp[col], xb[col]);
-              acc = fmaf(py, s_wp[DEC_H + col], acc);
-              acc = fmaf(pz, s_wp[2 * DEC_H + col], acc);
-              x0[u] = acc;
-              v[j + u] = __float_as_uint(acc);
+            for (int j = 0; j < 4; ++j) {
+              float x0 = fmaf(px[j], w0.x, xb.x), x1 = fmaf(px[j], w0.y, xb.y);
+              x0 = fmaf(py[j], w1.x, x0); x1 = fmaf(py[j], w1.y, x1);
+              x0 = fmaf(pz[j], w2.x, x0); x1 = fmaf(pz[j], w2.y, x1);
+              v[j >> 1][4 * i + 2 * (j & 1)] = __float_as_uint(x0);
+              v[j >> 1][4 * i + 2 * (j & 1) + 1] = __float_as_uint(x1);
+              const uint32_t pk = umma::pack_relu_bf16x2(fmaf(x0, ac.x, ac.z), fmaf(x1, ac.y, ac.w));
+              *reinterpret_cast<uint32_t *>(s_ah + kp * DEC_PANEL_A + (q * 32 + lr + 8 * j) * 128 +
+                                            (((hsel * 4 + i) ^ lr) << 4) + lc * 4) = pk;
             }
-            pk[j >> 1] = umma::pack_relu_bf16x2(fmaf(x0[0], a0[col0 + j], c0[col0 + j]),
-                                                fmaf(x0[1], a0[col0 + j + 1], c0[col0 + j + 1]));
           }
-          umma::tmem_st32(tmem_x + lane_base + col0, v);
-          uint8_t *rowp = s_ah + kp * DEC_PANEL_A + r * 128;
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const int cc = (hsel * 4 + c4) ^ (r & 7);
-            *reinterpret_cast<uint4 *>(rowp + (cc << 4)) = make_uint4(pk[c4 * 4], pk[c4 * 4 + 1], pk[c4 * 4 + 2], pk[c4 * 4 + 3]);
-          }
+          umma::tmem_st_16x256b_x4(tmem_x + lane_base + cb, v[0]);
+          umma::tmem_st_16x256b_x4(tmem_x + lane_base + (16u << 16) + cb, v[1]);
           umma::tc_wait_st();
           umma::fence_proxy_async_smem();
           umma::tc_fence_before();
@@ -220,29 +234,27 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
         umma::mbar_wait(&bars->acc_ready, layer_count & 1u);
         umma::tc_fence_after();
         const uint32_t src = ((l & 1) ? tmem_x : tmem_n) + lane_base;
-        const float *al = aff + (l + 1) * 2 * DEC_H, *cl = al + DEC_H;
+        const float4 *al = affi + (l + 1) * (DEC_H / 2);
         if (l < DEC_LAYERS - 1) {
 #pragma unroll 1
           for (int kp = 0; kp < DEC_KP; ++kp) {
-            const int col0 = kp * 64 + hsel * 32;
-            uint32_t v[32];
-            umma::tmem_ld32(src + col0, v);
+            const int cb = kp * 64 + hsel * 32;
+            uint32_t v[2][16];
+            umma::tmem_ld_16x256b_x4(src + cb, v[0]);
+            umma::tmem_ld_16x256b_x4(src + (16u << 16) + cb, v[1]);
             umma::tc_wait_ld();
-            uint32_t pk[16];
+            uint8_t *pan = s_ah + kp * DEC_PANEL_A + (q * 32 + lr) * 128 + lc * 4;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 a4 = *reinterpret_cast<const float4 *>(al + col0 + j);
-              const float4 c4 = *reinterpret_cast<const float4 *>(cl + col0 + j);
-              pk[(j >> 1)] = umma::pack_relu_bf16x2(fmaf(__uint_as_float(v[j]), a4.x, c4.x),
-                                                    fmaf(__uint_as_float(v[j + 1]), a4.y, c4.y));
-              pk[(j >> 1) + 1] = umma::pack_relu_bf16x2(fmaf(__uint_as_float(v[j + 2]), a4.z, c4.z),
-                                                        fmaf(__uint_as_float(v[j + 3]), a4.w, c4.w));
-            }
-            uint8_t *rowp = s_ah + kp * DEC_PANEL_A + r * 128;
+            for (int i = 0; i < 4; ++i) {
+              const float4 ac = al[(cb >> 1) + 4 * i + lc];
+              const int sw = ((hsel * 4 + i) ^ lr) << 4;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const int cc = (hsel * 4 + c4) ^ (r & 7);
-              *reinterpret_cast<uint4 *>(rowp + (cc << 4)) = make_uint4(pk[c4 * 4], pk[c4 * 4 + 1], pk[c4 * 4 + 2], pk[c4 * 4 + 3]);
+              for (int j = 0; j < 4; ++j) {
+                const float x0 = __uint_as_float(v[j >> 1][4 * i + 2 * (j & 1)]);
+                const float x1 = __uint_as_float(v[j >> 1][4 * i + 2 * (j & 1) + 1]);
+                *reinterpret_cast<uint32_t *>(pan + j * 8 * 128 + sw) =
+                    umma::pack_relu_bf16x2(fmaf(x0, ac.x, ac.z), fmaf(x1, ac.y, ac.w));
+              }
             }
             umma::fence_proxy_async_smem();
             umma::tc_fence_before();
@@ -251,24 +263,42 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
           }
         } else {
           // final: logits = fc_out(relu(cbn(x)))  -- fp32 dot product over the 256 channels
-          float part = 0.f;
+          float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
           for (int kp = 0; kp < DEC_KP; ++kp) {
-            const int col0 = kp * 64 + hsel * 32;
-            uint32_t v[32];
-            umma::tmem_ld32(src + col0, v);
+            const int cb = kp * 64 + hsel * 32;
+            uint32_t v[2][16];
+            umma::tmem_ld_16x256b_x4(src + cb, v[0]);
+            umma::tmem_ld_16x256b_x4(src + (16u << 16) + cb, v[1]);
             umma::tc_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float h = fmaxf(fmaf(__uint_as_float(v[j]), al[col0 + j], cl[col0 + j]), 0.f);
-              part = fmaf(h, s_wout[col0 + j], part);
+            for (int i = 0; i < 4; ++i) {
+              const float4 ac = al[(cb >> 1) + 4 * i + lc];
+              const float2 wo = *reinterpret_cast<const float2 *>(s_wout + cb + 8 * i + 2 * lc);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float x0 = __uint_as_float(v[j >> 1][4 * i + 2 * (j & 1)]);
+                const float x1 = __uint_as_float(v[j >> 1][4 * i + 2 * (j & 1) + 1]);
+                part[j] = fmaf(fmaxf(fmaf(x0, ac.x, ac.z), 0.f), wo.x, part[j]);
+                part[j] = fmaf(fmaxf(fmaf(x1, ac.y, ac.w), 0.f), wo.y, part[j]);
+              }
             }
           }
-          s_out[hsel * DEC_TILE_M + r] = part;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            part[j] += __shfl_xor_sync(0xffffffffu, part[j], 1);
+            part[j] += __shfl_xor_sync(0xffffffffu, part[j], 2);
+            if (lc == 0) s_out[hsel * DEC_TILE_M + q * 32 + lr + 8 * j] = part[j];
+          }
           umma::tc_fence_before();
           asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
-          if (hsel == 0 && valid)
-            logits[(size_t)obj * T + t] = (s_out[r] + s_out[DEC_TILE_M + r]) + fc_out_b;
+          if (hsel == 0 && lc == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int t = t0 + 8 * j, rr = q * 32 + lr + 8 * j;
+              if (t < T) logits[(size_t)obj * T + t] = (s_out[rr] + s_out[DEC_TILE_M + rr]) + fc_out_b;
+            }
+          }
         }
       }
       __syncwarp();
@@ -361,10 +391,13 @@ onet_cbn_tables_kernel(const float *__restrict__ c, int B, int c_dim, const floa
       }
       const float a = gam * rsqrtf(__ldg(run_var + l * DEC_H + ch) + eps);
       const float cc = fmaf(a, pend - __ldg(run_mean + l * DEC_H + ch), bet);
-      float *rec = aff + (size_t)(b0 + lane) * DEC_AFF_FLOATS;
+      float *rec = aff + (size_t)(b0 + lane) * DEC_REC_FLOATS;
       rec[l * 2 * DEC_H + ch] = a;
       rec[l * 2 * DEC_H + DEC_H + ch] = cc;
-      if (l == 0) rec[DEC_CBN * 2 * DEC_H + ch] = __ldg(x_bias + (size_t)(b0 + lane) * DEC_H + ch);
+      if (l == 0) rec[DEC_PLAIN_FLOATS + ch] = __ldg(x_bias + (size_t)(b0 + lane) * DEC_H + ch);
+      float *pr = rec + DEC_PLAIN_FLOATS + DEC_H + l * 2 * DEC_H + (ch >> 1) * 4 + (ch & 1);
+      pr[0] = a;
+      pr[2] = cc;
     }
   }
 }
@@ -377,7 +410,7 @@ __global__ void dec_fcp_kernel(const float *__restrict__ p, long long p_stride, 
   const int o = blockIdx.y, bl = blockIdx.z;  // bl: object within chunk
   if (t >= T) return;
   const float *pp = p + (size_t)(b0 + bl) * p_stride + (size_t)t * 3;
-  const float xb = __ldg(aff + (size_t)(b0 + bl) * DEC_AFF_FLOATS + DEC_CBN * 2 * DEC_H + o);
+  const float xb = __ldg(aff + (size_t)(b0 + bl) * DEC_REC_FLOATS + DEC_PLAIN_FLOATS + o);
   float acc = fmaf(__ldg(pp), __ldg(fc_p_w + o * 3), xb);
   acc = fmaf(__ldg(pp + 1), __ldg(fc_p_w + o * 3 + 1), acc);
   acc = fmaf(__ldg(pp + 2), __ldg(fc_p_w + o * 3 + 2), acc);
@@ -389,7 +422,7 @@ __global__ void dec_out_kernel(const float *__restrict__ x, int T, const float *
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int bl = blockIdx.y;
   if (t >= T) return;
-  const float *rec = aff + (size_t)(b0 + bl) * DEC_AFF_FLOATS + 10 * 2 * DEC_H;
+  const float *rec = aff + (size_t)(b0 + bl) * DEC_REC_FLOATS + 10 * 2 * DEC_H;
   float acc = 0.f;
   for (int k = 0; k < DEC_H; ++k) {
     const float h = fmaxf(fmaf(__ldg(x + ((size_t)bl * DEC_H + k) * T + t), __ldg(rec + k), __ldg(rec + DEC_H + k)), 0.f);
@@ -454,7 +487,7 @@ extern "C" size_t rfd_onet_packed_bytes(int nsplit) {
   return nsplit == 1 ? (size_t)DEC_LAYERS * DEC_KP * DEC_STAGE_B : 0;
 }
 
-extern "C" size_t rfd_onet_aff_floats(void) { return DEC_AFF_FLOATS; }
+extern "C" size_t rfd_onet_aff_floats(void) { return DEC_REC_FLOATS; }
 
 extern "C" int rfd_onet_pack_weights(const float *fc_w, int nsplit, void *packed, void *stream) {
   if (!fc_w || !packed) return RFD_ERR_INVALID_ARGUMENT;
@@ -532,16 +565,16 @@ extern "C" int rfd_onet_decode_f32(const float *p, long long p_batch_stride, int
     float *x = workspace, *net = workspace + (size_t)bc * DEC_H * T;
     dec_fcp_kernel<<<dim3(h_ceil_div(T, 256), DEC_H, nb), 256, 0, st>>>(p, p_batch_stride, T, fc_p_w, aff, b0, x);
     RFD_CHECK_LAUNCH("dec_fcp_kernel");
-    const float *affb = aff + (size_t)b0 * DEC_AFF_FLOATS;
+    const float *affb = aff + (size_t)b0 * DEC_REC_FLOATS;
     for (int i = 0; i < 5; ++i) {
       // net = W_{2i} . relu(a_{2i} x + c_{2i})
       int rc = launch_pointwise_f32(x, fc_w + (size_t)(2 * i) * DEC_H * DEC_H, ones_zeros, ones_zeros + DEC_H, nullptr,
-                                    affb + (2 * i) * 2 * DEC_H, affb + (2 * i) * 2 * DEC_H + DEC_H, DEC_AFF_FLOATS, 0, 1,
+                                    affb + (2 * i) * 2 * DEC_H, affb + (2 * i) * 2 * DEC_H + DEC_H, DEC_REC_FLOATS, 0, 1,
                                     nb, DEC_H, DEC_H, T, net, st);
       if (rc != RFD_OK) return rc;
       // x = x + W_{2i+1} . relu(a_{2i+1} net + c_{2i+1})     (in place: each element read then written by one thread)
       rc = launch_pointwise_f32(net, fc_w + (size_t)(2 * i + 1) * DEC_H * DEC_H, ones_zeros, ones_zeros + DEC_H, x,
-                                affb + (2 * i + 1) * 2 * DEC_H, affb + (2 * i + 1) * 2 * DEC_H + DEC_H, DEC_AFF_FLOATS,
+                                affb + (2 * i + 1) * 2 * DEC_H, affb + (2 * i + 1) * 2 * DEC_H + DEC_H, DEC_REC_FLOATS,
                                 0, 1, nb, DEC_H, DEC_H, T, x, st);
       if (rc != RFD_OK) return rc;
     }

@@ -181,6 +181,8 @@ class DecoderCBatchNorm(nn.Module):
         with torch.cuda.device(c.device):
             st = torch.cuda.current_stream().cuda_stream
             if precision == 'bf16':
+              # algorithmic FLOP: 2*(3*256 + 10*256*256 + 256) per query point
+              with _lib.timed("onet_decode", float(B) * T * 1312768.0):
                 _lib.check(lib.rfd_onet_decode(p.data_ptr(), stride, B, T, P['fc_p_w'].data_ptr(),
                                                P['packed'].data_ptr(), 1, aff.data_ptr(), P['fc_out_w'].data_ptr(),
                                                P['fc_out_b'], logits.data_ptr(), st), "onet_decode")

@@ -128,7 +128,9 @@ def fused_query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz=True,
     out = torch.empty((B, Ct, M, nsample), dtype=torch.float32, device=dev)
     gxyz = torch.empty((B, 3, M, nsample), dtype=torch.float32, device=dev) if ret_grouped_xyz else None
     idx = torch.empty((B, M, nsample), dtype=torch.int32, device=dev) if ret_idx else None
-    with torch.cuda.device(dev):
+    # algorithmic HBM bytes: 12N + 12M + 4CN + 4(3+C)MS (+ 4MS when idx is written)
+    work = B * (12 * N + 12 * M + 4 * C * N + 4 * Ct * M * nsample + (4 * M * nsample if ret_idx else 0))
+    with torch.cuda.device(dev), _lib.timed("query_and_group", work):
         _lib.check(_lib.load().rfd_query_and_group(
             xyz.data_ptr(), new_xyz.data_ptr(), 0 if features is None else features.data_ptr(), B, N, M, C,
             float(radius), int(nsample), int(bool(use_xyz)), int(bool(normalize_xyz)), out.data_ptr(),

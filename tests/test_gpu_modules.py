@@ -1,0 +1,91 @@
+"""GPU tests of the module-level hot path (SA / FP / voting / proposal mirrors on the sm_100a kernels) against
+oracle/model_ref (CPU) and the golden fixtures produced by the reference's own Python modules."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref
+from rfdnet_b200 import detection, pointnet2_modules
+from rfdnet_b200.synth import scannet_like_batch, seeded_fill, uniform_cloud
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_sa_module_fused_vs_oracle_and_golden(golden):
+    sa = pointnet2_modules.PointnetSAModuleVotes(npoint=128, radius=0.3, nsample=16, mlp=[5, 32, 32, 64],
+                                                 use_xyz=True, normalize_xyz=True).eval()
+    seeded_fill(sa, 11)
+    g = torch.Generator().manual_seed(3)
+    xyz = torch.from_numpy(uniform_cloud(2, 1024, seed=5))
+    feats = torch.randn(2, 5, 1024, generator=g)
+    sd = {"sa." + k: v for k, v in sa.state_dict().items()}
+    rx, rf, ri = model_ref.sa_module(xyz, feats, sd, "sa", 128, 0.3, 16, recip=True)
+    sa = sa.to(DEV)
+    with torch.no_grad():
+        nx, nf, ind = sa(xyz.to(DEV), feats.to(DEV))
+    assert np.array_equal(ind.cpu().numpy(), golden["sa_inds"]) and torch.equal(ind.cpu(), ri)
+    assert np.array_equal(nx.cpu().numpy(), golden["sa_new_xyz"])
+    assert torch.allclose(nf.cpu(), rf, atol=1e-4, rtol=1e-4)
+    assert np.allclose(nf.cpu().numpy(), golden["sa_new_features"], atol=1e-4, rtol=1e-4)
+    # training-mode path = reference sequence on the drop-in ops + cuDNN (TF32 off: torch's default would be the
+    # less accurate side): same numbers as the fused fp32 kernels
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sa_ref_path = sa._forward_reference(xyz.to(DEV), feats.to(DEV), None)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert torch.equal(sa_ref_path[2], ind)
+    assert torch.allclose(sa_ref_path[1], nf, atol=1e-4, rtol=1e-4)
+
+
+def test_fp_module_vs_golden(golden):
+    fp = pointnet2_modules.PointnetFPModule(mlp=[64 + 16, 64, 32]).eval()
+    seeded_fill(fp, 12)
+    g = torch.Generator().manual_seed(3)
+    _ = torch.randn(2, 5, 1024, generator=g)  # keep the generator in step with make_golden.py
+    unk = torch.from_numpy(uniform_cloud(2, 300, seed=6)).to(DEV)
+    kn = torch.from_numpy(uniform_cloud(2, 64, seed=7)).to(DEV)
+    uf, kf = torch.randn(2, 16, 300, generator=g).to(DEV), torch.randn(2, 64, 64, generator=g).to(DEV)
+    fp = fp.to(DEV)
+    with torch.no_grad():
+        out = fp(unk, kn, uf, kf)
+    assert np.allclose(out.cpu().numpy(), golden["fp_out"], atol=1e-4, rtol=1e-4)
+
+
+def test_detection_hot_path_vs_golden(golden):
+    net = detection.DetectionHotPath(1, 256).eval()
+    seeded_fill(net.backbone, 21)
+    seeded_fill(net.voting, 22)
+    seeded_fill(net.detection, 23)
+    net = net.to(DEV)
+    pc = torch.from_numpy(scannet_like_batch(1, 20000, seed0=100)).to(DEV)
+    with torch.no_grad():
+        ep, _ = net(pc)
+    assert np.array_equal(ep["sa1_inds"].cpu().numpy(), golden["det_sa1_inds"])
+    assert np.array_equal(ep["aggregated_vote_inds"].cpu().numpy(), golden["det_agg_inds"])
+    # golden was produced on CPU (true division by the radius), the GPU path multiplies by 1/r like torch-CUDA:
+    # features agree to fp32 round-off
+    assert np.allclose(ep["sa4_features"].cpu().numpy()[:, :, :32], golden["det_sa4_features"], atol=1e-4, rtol=1e-4)
+    assert np.allclose(ep["fp2_features"].cpu().numpy()[:, :, :64], golden["det_fp2_features"], atol=1e-4, rtol=1e-4)
+    assert np.allclose(ep["vote_xyz"].cpu().numpy()[:, :128], golden["det_vote_xyz"], atol=1e-4, rtol=1e-4)
+    assert np.allclose(ep["objectness_scores"].cpu().numpy(), golden["det_objectness"], atol=2e-4, rtol=1e-3)
+    assert np.allclose(ep["center"].cpu().numpy(), golden["det_center"], atol=2e-4, rtol=1e-3)
+    assert np.allclose(ep["sem_cls_scores"].cpu().numpy(), golden["det_sem_cls"], atol=2e-4, rtol=1e-3)
+
+
+def test_detection_80k_batch_shapes_and_determinism():
+    net = detection.DetectionHotPath(1, 256).eval()
+    seeded_fill(net, 5)
+    net = net.to(DEV)
+    pc = torch.from_numpy(scannet_like_batch(2, 80000, seed0=7)).to(DEV)
+    with torch.no_grad():
+        ep, _ = net(pc)
+        ep2, _ = net(pc)
+    assert ep["sa1_xyz"].shape == (2, 2048, 3) and ep["fp2_features"].shape == (2, 256, 1024)
+    assert ep["objectness_scores"].shape == (2, 256, 2) and ep["center"].shape == (2, 256, 3)
+    assert torch.equal(ep["sa2_inds"][0].long().cpu(), torch.arange(1024))
+    for k in ("sa1_inds", "fp2_features", "center", "sem_cls_scores"):
+        assert torch.equal(ep[k], ep2[k]), k  # no atomics on the forward path: bitwise reproducible
+    assert torch.isfinite(ep["center"]).all()

@@ -32,7 +32,7 @@ def test_cabi_exports_every_declared_symbol(lib):
     assert lib.rfd_ball_query(None, None, 1, 10, 10, 0.1, 4, None, None) == -1
     assert lib.rfd_onet_decode(None, 0, 1, 128, None, None, 3, None, None, 0.0, None, None) == -1
     assert lib.rfd_onet_packed_bytes(1) == 10 * 4 * 256 * 128
-    assert lib.rfd_onet_aff_floats() == 11 * 2 * 256 + 256
+    assert lib.rfd_onet_aff_floats() == 2 * 11 * 2 * 256 + 256
 
 
 def test_no_oracle_import_in_product():
