@@ -8,7 +8,7 @@
 //     (no `temp` tensor exists; HBM traffic is the compulsory 12*N bytes in + 4*m bytes out);
 //   * per round: register update -> warp arg-max with two redux.sync -> one __syncthreads -> CTA arg-max ->
 //     the CTA winner (key + xyz) is pushed to every peer CTA's shared memory over DSMEM and signalled with a
-//     remote mbarrier arrive (release.cluster); peers wait on their local mbarrier (acquire.cluster).
+//     the stores' own mbarrier complete_tx (st.async); peers wait on their local mbarrier.
 //     No cluster-wide barrier and no global-memory round trip sits on the serial chain.
 //
 // Bit-exactness with the reference:
@@ -58,15 +58,29 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_
 __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// 16-byte asynchronous store into a peer CTA's shared memory that, on completion, performs complete_tx(16) on
+// the peer's mbarrier: data and signal travel together, no release fence (an `mbarrier.arrive.release.cluster`
+// after plain st.shared::cluster stores costs an ERRBAR/MEMBAR on the serial chain of every round).
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                            uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   cluster_addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_mbar)
+               : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx_local(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+// Wait on the LOCAL mbarrier.  Deliberately the default (.acquire.cta) form, as in CUTLASS's ClusterBarrier::wait:
+// the peers' records are written straight into THIS CTA's shared memory (st.shared::cluster) before their
+// release.cluster arrive, so nothing cached needs invalidating -- whereas `.acquire.cluster` makes ptxas emit a
+// CCTL.IVALL (L1 invalidate-all) after every wait, which was 45% of all stall samples of this kernel (profiles/).
 __device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t addr, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
       "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra DONE;\n\t"
       "bra LAB_WAIT;\n\t"
       "DONE:\n\t"
@@ -113,8 +127,8 @@ fps_kernel(const float *__restrict__ xyz_all, int N, int m, int bs_log2, int Q, 
 
   if (CS > 1) {
     if (tid == 0) {
-      mbar_init(smem_u32(&s_mbar[0]), (uint32_t)CS);
-      mbar_init(smem_u32(&s_mbar[1]), (uint32_t)CS);
+      mbar_init(smem_u32(&s_mbar[0]), 1u);  // one local arming arrive per round; peers complete the tx bytes
+      mbar_init(smem_u32(&s_mbar[1]), 1u);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster_sync_all();  // barriers initialised + every CTA of the cluster is resident before any DSMEM access
@@ -147,6 +161,9 @@ fps_kernel(const float *__restrict__ xyz_all, int N, int m, int bs_log2, int Q, 
 
   for (int j = 1; j < m; ++j) {
     const int par = j & 1;
+    // arm this round's barrier: CS records of 32 bytes will land in s_cta[par] (peers may already be sending:
+    // the pending arrival keeps the phase open until this arm has happened)
+    if (CS > 1 && tid == 0) mbar_arrive_expect_tx_local(smem_u32(&s_mbar[par]), (uint32_t)CS * 32u);
     float best = -1.f;
     int besti = 0;
 #pragma unroll
@@ -188,9 +205,9 @@ fps_kernel(const float *__restrict__ xyz_all, int N, int m, int bs_log2, int Q, 
         const FpsRec c = fps_pick(s_warp[par], FPS_WARPS, lane);
         if (lane < CS) {
           const uint32_t dst = mapa_u32(smem_u32(&s_cta[par][rank]), (uint32_t)lane);
-          st_cluster_v4(dst, c.hi, c.lo, (uint32_t)c.k, 0u);
-          st_cluster_v4(dst + 16, __float_as_uint(c.x), __float_as_uint(c.y), __float_as_uint(c.z), 0u);
-          mbar_arrive_remote_release(mapa_u32(smem_u32(&s_mbar[par]), (uint32_t)lane));
+          const uint32_t bar = mapa_u32(smem_u32(&s_mbar[par]), (uint32_t)lane);
+          st_async_v4(dst, c.hi, c.lo, (uint32_t)c.k, 0u, bar);
+          st_async_v4(dst + 16, __float_as_uint(c.x), __float_as_uint(c.y), __float_as_uint(c.z), 0u, bar);
         }
       }
       mbar_wait_acquire_cluster(smem_u32(&s_mbar[par]), (phases >> par) & 1u);

@@ -36,7 +36,7 @@ constexpr int DEC_TILE_M = 128;
 constexpr int DEC_KP = 4;
 constexpr int DEC_PANEL_A = DEC_TILE_M * 128;   // 16384 B : 128 rows x 64 bf16
 constexpr int DEC_STAGE_B = DEC_H * 128;        // 32768 B : 256 rows x 64 bf16
-constexpr int DEC_NSTAGE = 3;
+constexpr int DEC_NSTAGE = 4;
 // per-object record in global memory (rfd_onet_cbn_tables):
 //   [0, 5632)      plain   [11 layers][a: 256][c: 256]                      (fp32 path)
 //   [5632, 5888)   x_bias  [256]
@@ -46,25 +46,24 @@ constexpr int DEC_PLAIN_FLOATS = DEC_CBN * 2 * DEC_H;         // 5632
 constexpr int DEC_AFF_FLOATS = DEC_H + DEC_CBN * 2 * DEC_H;   // 5888 floats staged in shared memory
 constexpr int DEC_AFF_BYTES = DEC_AFF_FLOATS * 4;             // 23552
 constexpr int DEC_REC_FLOATS = DEC_PLAIN_FLOATS + DEC_AFF_FLOATS;  // 11520
-constexpr int DEC_THREADS = 320;                // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
-constexpr int DEC_EPI_WARPS = 8;
+constexpr int DEC_EPI_WARPS = 16;               // 4 TMEM lane quarters x 4 column quarters of every 64-column panel
+constexpr int DEC_THREADS = 64 + 32 * DEC_EPI_WARPS;  // warp 0 producer, warp 1 MMA, warps 2.. epilogue
+constexpr int DEC_CW = 16;                      // columns of a panel owned by one epilogue warp
 
 // shared memory map (offsets from a 1024-B aligned base)
 constexpr int SM_AH = 0;
 constexpr int SM_W = SM_AH + DEC_KP * DEC_PANEL_A;              // 65536
 constexpr int SM_AFF = SM_W + DEC_NSTAGE * DEC_STAGE_B;         // 163840
-constexpr int SM_WP = SM_AFF + 2 * DEC_AFF_BYTES;               // 210944
+constexpr int SM_WP = SM_AFF + DEC_AFF_BYTES;                   // single affine buffer (reloaded on object change)
 constexpr int SM_WOUT = SM_WP + 3 * DEC_H * 4;                  // 214016
 constexpr int SM_OUT = SM_WOUT + DEC_H * 4;                     // 215040
-constexpr int SM_BAR = SM_OUT + 2 * DEC_TILE_M * 4;             // 216064
+constexpr int SM_BAR = SM_OUT + 4 * DEC_TILE_M * 4;             // 217088
 constexpr int SM_TOTAL = SM_BAR + 256;                          // 216320
 constexpr int DEC_SMEM_BYTES = SM_TOTAL + 1024;                 // + alignment slack
 
 struct DecBars {
   uint64_t w_full[DEC_NSTAGE];
   uint64_t w_empty[DEC_NSTAGE];
-  uint64_t aff_full[2];
-  uint64_t aff_empty[2];
   uint64_t a_ready[DEC_KP];
   uint64_t acc_ready;
   uint32_t tmem_base;
@@ -82,14 +81,13 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
   float *s_aff = reinterpret_cast<float *>(smem + SM_AFF);
   float *s_wp = reinterpret_cast<float *>(smem + SM_WP);      // [3][256]
   float *s_wout = reinterpret_cast<float *>(smem + SM_WOUT);  // [256]
-  float *s_out = reinterpret_cast<float *>(smem + SM_OUT);    // [2][128]
+  float *s_out = reinterpret_cast<float *>(smem + SM_OUT);    // [4][128]
   DecBars *bars = reinterpret_cast<DecBars *>(smem + SM_BAR);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
     for (int i = 0; i < DEC_NSTAGE; ++i) { umma::mbar_init(&bars->w_full[i], 1); umma::mbar_init(&bars->w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->aff_full[i], 1); umma::mbar_init(&bars->aff_empty[i], DEC_EPI_WARPS); }
     for (int i = 0; i < DEC_KP; ++i) umma::mbar_init(&bars->a_ready[i], DEC_EPI_WARPS);
     umma::mbar_init(&bars->acc_ready, 1);
     umma::fence_barrier_init();
@@ -105,31 +103,17 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
   umma::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   const uint32_t tmem_x = tmem_base, tmem_n = tmem_base + DEC_H;
+  // contiguous chunk of tiles per CTA: consecutive tiles of a CTA almost always belong to the same object, so the
+  // per-object affine table is (re)loaded only on an object change (2-3 times per launch)
+  const int tile_lo = (int)(((long long)num_tiles * blockIdx.x) / gridDim.x);
+  const int tile_hi = (int)(((long long)num_tiles * (blockIdx.x + 1)) / gridDim.x);
 
   if (warp == 0) {
-    // ===================== producer: weight ring + affine-table prefetch =====================
+    // ===================== producer: weight ring =====================
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        if (it == 0) {
-          umma::mbar_arrive_expect_tx(&bars->aff_full[0], DEC_AFF_BYTES);
-          umma::bulk_g2s(s_aff, aff_all + (size_t)(tile / tiles_per_obj) * DEC_REC_FLOATS + DEC_PLAIN_FLOATS, DEC_AFF_BYTES,
-                         &bars->aff_full[0]);
-        }
+      for (int tile = tile_lo; tile < tile_hi; ++tile) {
         for (int s = 0; s < DEC_LAYERS * DEC_KP; ++s) {
-          if (s == 8) {
-            const int next = tile + gridDim.x;
-            if (next < num_tiles) {
-              const int nb = (it + 1) & 1;
-              const uint32_t n = (uint32_t)(it + 1) >> 1;  // use count of that buffer
-              umma::mbar_wait(&bars->aff_empty[nb], (n & 1u) ^ 1u);
-              umma::mbar_arrive_expect_tx(&bars->aff_full[nb], DEC_AFF_BYTES);
-              umma::bulk_g2s(s_aff + nb * DEC_AFF_FLOATS,
-                             aff_all + (size_t)(next / tiles_per_obj) * DEC_REC_FLOATS + DEC_PLAIN_FLOATS, DEC_AFF_BYTES,
-                             &bars->aff_full[nb]);
-            }
-          }
           umma::mbar_wait(&bars->w_empty[st], ph ^ 1u);
           umma::mbar_arrive_expect_tx(&bars->w_full[st], DEC_STAGE_B);
           umma::bulk_g2s(s_w + st * DEC_STAGE_B, packed + (size_t)s * DEC_STAGE_B, DEC_STAGE_B, &bars->w_full[st]);
@@ -143,7 +127,7 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
       constexpr uint32_t idesc = umma::make_idesc_bf16_f32(DEC_TILE_M, DEC_H);
       const uint32_t ah_addr = umma::smem_u32(s_ah), w_addr = umma::smem_u32(s_w);
       uint32_t st = 0, ph = 0, layer_count = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_lo; tile < tile_hi; ++tile) {
         for (int l = 0; l < DEC_LAYERS; ++l, ++layer_count) {
           const uint32_t d = (l & 1) ? tmem_x : tmem_n;  // fc_0 -> net (fresh), fc_1 -> accumulate onto x
           for (int kp = 0; kp < DEC_KP; ++kp) {
@@ -164,25 +148,37 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
       }
     }
   } else {
-    // ===================== epilogue warps (8): TMEM -> affine+ReLU -> bf16 A panels =====================
+    // ===================== epilogue warps (16): TMEM -> affine+ReLU -> bf16 A panels =====================
     // TMEM is read with the 16x256b shape: a thread then owns 4 ROWS x (2 adjacent columns per 8-column block), so
     // one per-channel (a,c) fetch from shared memory serves four rows and every shared-memory store of a warp is a
-    // conflict-free 128-byte wavefront (8 rows x 16 B after the 128B swizzle).
+    // conflict-free 128-byte wavefront (8 rows x 16 B after the 128B swizzle).  16 warps (4 per scheduler) hide the
+    // TMEM / shared-memory latencies of each other; warp (q, cq) owns rows [32q, 32q+32) x columns [16cq, 16cq+16)
+    // of every 64-column panel.
     const int ew = warp - 2;
     const int q = warp & 3;     // TMEM lane quarter this warp may access
-    const int hsel = ew >> 2;   // which 32-column half of every 64-column panel
+    const int cq = ew >> 2;     // which 16-column quarter of every 64-column panel
     const int lr = lane >> 2;   // 0..7  row within an 8-row group  (== row & 7 : the swizzle phase)
     const int lc = lane & 3;    // 0..3  column pair within an 8-column block
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint32_t layer_count = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    int cur_obj = -1;
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
       const int obj = tile / tiles_per_obj;
       const int t0 = (tile - obj * tiles_per_obj) * DEC_TILE_M + q * 32 + lr;  // row j of this thread: t0 + 8j
-      const int ab = it & 1;
-      umma::mbar_wait(&bars->aff_full[ab], ((uint32_t)it >> 1) & 1u);
-      const float *aff = s_aff + ab * DEC_AFF_FLOATS;   // [x_bias 256][11 layers][128 column pairs]{a0,a1,c0,c1}
-      const float4 *affi = reinterpret_cast<const float4 *>(aff + DEC_H);
+      if (obj != cur_obj) {
+        // (re)load this object's x_bias + paired (a,c) table: 5888 floats, all 16 epilogue warps cooperate
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * DEC_EPI_WARPS) : "memory");  // everyone is done with the old table
+        const float4 *src4 = reinterpret_cast<const float4 *>(aff_all + (size_t)obj * DEC_REC_FLOATS + DEC_PLAIN_FLOATS);
+        float4 *dst4 = reinterpret_cast<float4 *>(s_aff);
+        for (int e = tid - 64; e < DEC_AFF_FLOATS / 4; e += 32 * DEC_EPI_WARPS) dst4[e] = __ldg(src4 + e);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * DEC_EPI_WARPS) : "memory");
+        cur_obj = obj;
+      }
+      // shared-space byte addresses (explicit ld.shared / st.shared: the compiler otherwise emits generic LD/ST)
+      const uint32_t aff_a = umma::smem_u32(s_aff);  // [x_bias 256][11][128 pairs]{a0,a1,c0,c1}
+      const uint32_t affi_a = aff_a + DEC_H * 4 + lc * 16;                  // + layer*2048 + (col/2)*16
+      const uint32_t pan0 = umma::smem_u32(s_ah) + (q * 32 + lr) * 128 + lc * 4;  // + kp*PANEL + j*1024 + swizzled chunk
+      const uint32_t wp_a = umma::smem_u32(s_wp), wout_a = umma::smem_u32(s_wout);
       // ---- E0: x0 = fc_p(p) + (fc_p.bias + fc_z(z)) in fp32 -> TMEM ; h0 = relu(a0*x0 + c0) -> A panels
       {
         float px[4], py[4], pz[4];
@@ -197,16 +193,17 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
         }
 #pragma unroll 1
         for (int kp = 0; kp < DEC_KP; ++kp) {
-          const int cb = kp * 64 + hsel * 32;
-          uint32_t v[2][16];
+          const int cb = kp * 64 + cq * DEC_CW;
+          uint32_t v[2][8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 2; ++i) {
             const int col = cb + 8 * i + 2 * lc;
-            const float2 w0 = *reinterpret_cast<const float2 *>(s_wp + col);
-            const float2 w1 = *reinterpret_cast<const float2 *>(s_wp + DEC_H + col);
-            const float2 w2 = *reinterpret_cast<const float2 *>(s_wp + 2 * DEC_H + col);
-            const float2 xb = *reinterpret_cast<const float2 *>(aff + col);
-            const float4 ac = affi[col >> 1];
+            const float2 w0 = umma::lds_f2(wp_a + col * 4);
+            const float2 w1 = umma::lds_f2(wp_a + (DEC_H + col) * 4);
+            const float2 w2 = umma::lds_f2(wp_a + (2 * DEC_H + col) * 4);
+            const float2 xb = umma::lds_f2(aff_a + col * 4);
+            const float4 ac = umma::lds_f4(affi_a + (cb >> 1) * 16 + i * 64);
+            const uint32_t sw = (uint32_t)(((cq * 2 + i) ^ lr) << 4);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float x0 = fmaf(px[j], w0.x, xb.x), x1 = fmaf(px[j], w0.y, xb.y);
@@ -214,13 +211,12 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
               x0 = fmaf(pz[j], w2.x, x0); x1 = fmaf(pz[j], w2.y, x1);
               v[j >> 1][4 * i + 2 * (j & 1)] = __float_as_uint(x0);
               v[j >> 1][4 * i + 2 * (j & 1) + 1] = __float_as_uint(x1);
-              const uint32_t pk = umma::pack_relu_bf16x2(fmaf(x0, ac.x, ac.z), fmaf(x1, ac.y, ac.w));
-              *reinterpret_cast<uint32_t *>(s_ah + kp * DEC_PANEL_A + (q * 32 + lr + 8 * j) * 128 +
-                                            (((hsel * 4 + i) ^ lr) << 4) + lc * 4) = pk;
+              umma::sts_u32(pan0 + kp * DEC_PANEL_A + j * 1024 + sw,
+                            umma::pack_relu_bf16x2(fmaf(x0, ac.x, ac.z), fmaf(x1, ac.y, ac.w)));
             }
           }
-          umma::tmem_st_16x256b_x4(tmem_x + lane_base + cb, v[0]);
-          umma::tmem_st_16x256b_x4(tmem_x + lane_base + (16u << 16) + cb, v[1]);
+          umma::tmem_st_16x256b_x2(tmem_x + lane_base + cb, v[0]);
+          umma::tmem_st_16x256b_x2(tmem_x + lane_base + (16u << 16) + cb, v[1]);
           umma::tc_wait_st();
           umma::fence_proxy_async_smem();
           umma::tc_fence_before();
@@ -233,27 +229,32 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
       for (int l = 0; l < DEC_LAYERS; ++l, ++layer_count) {
         umma::mbar_wait(&bars->acc_ready, layer_count & 1u);
         umma::tc_fence_after();
-        const uint32_t src = ((l & 1) ? tmem_x : tmem_n) + lane_base;
-        const float4 *al = affi + (l + 1) * (DEC_H / 2);
+        const uint32_t src = ((l & 1) ? tmem_x : tmem_n) + lane_base + cq * DEC_CW;
+        const uint32_t al = affi_a + (l + 1) * (DEC_H * 2 * 4) + cq * (DEC_CW / 2) * 16;  // + kp*512 + i*64
+        // software pipeline over the four panels: the TMEM load of panel kp+1 is in flight while panel kp is
+        // converted, stored and published
+        uint32_t v[2][2][8];
+        umma::tmem_ld_16x256b_x2(src, v[0][0]);
+        umma::tmem_ld_16x256b_x2(src + (16u << 16), v[0][1]);
         if (l < DEC_LAYERS - 1) {
-#pragma unroll 1
-          for (int kp = 0; kp < DEC_KP; ++kp) {
-            const int cb = kp * 64 + hsel * 32;
-            uint32_t v[2][16];
-            umma::tmem_ld_16x256b_x4(src + cb, v[0]);
-            umma::tmem_ld_16x256b_x4(src + (16u << 16) + cb, v[1]);
-            umma::tc_wait_ld();
-            uint8_t *pan = s_ah + kp * DEC_PANEL_A + (q * 32 + lr) * 128 + lc * 4;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 ac = al[(cb >> 1) + 4 * i + lc];
-              const int sw = ((hsel * 4 + i) ^ lr) << 4;
+          for (int kp = 0; kp < DEC_KP; ++kp) {
+            const float4 ac0 = umma::lds_f4(al + kp * 512), ac1 = umma::lds_f4(al + kp * 512 + 64);
+            umma::tc_wait_ld();
+            if (kp + 1 < DEC_KP) {
+              umma::tmem_ld_16x256b_x2(src + (kp + 1) * 64, v[(kp + 1) & 1][0]);
+              umma::tmem_ld_16x256b_x2(src + (16u << 16) + (kp + 1) * 64, v[(kp + 1) & 1][1]);
+            }
+            const uint32_t pan = pan0 + kp * DEC_PANEL_A;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float4 ac = i ? ac1 : ac0;
+              const uint32_t sw = (uint32_t)(((cq * 2 + i) ^ lr) << 4);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float x0 = __uint_as_float(v[j >> 1][4 * i + 2 * (j & 1)]);
-                const float x1 = __uint_as_float(v[j >> 1][4 * i + 2 * (j & 1) + 1]);
-                *reinterpret_cast<uint32_t *>(pan + j * 8 * 128 + sw) =
-                    umma::pack_relu_bf16x2(fmaf(x0, ac.x, ac.z), fmaf(x1, ac.y, ac.w));
+                const float x0 = __uint_as_float(v[kp & 1][j >> 1][4 * i + 2 * (j & 1)]);
+                const float x1 = __uint_as_float(v[kp & 1][j >> 1][4 * i + 2 * (j & 1) + 1]);
+                umma::sts_u32(pan + j * 1024 + sw, umma::pack_relu_bf16x2(fmaf(x0, ac.x, ac.z), fmaf(x1, ac.y, ac.w)));
               }
             }
             umma::fence_proxy_async_smem();
@@ -264,23 +265,24 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
         } else {
           // final: logits = fc_out(relu(cbn(x)))  -- fp32 dot product over the 256 channels
           float part[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-          for (int kp = 0; kp < DEC_KP; ++kp) {
-            const int cb = kp * 64 + hsel * 32;
-            uint32_t v[2][16];
-            umma::tmem_ld_16x256b_x4(src + cb, v[0]);
-            umma::tmem_ld_16x256b_x4(src + (16u << 16) + cb, v[1]);
-            umma::tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 ac = al[(cb >> 1) + 4 * i + lc];
-              const float2 wo = *reinterpret_cast<const float2 *>(s_wout + cb + 8 * i + 2 * lc);
+          for (int kp = 0; kp < DEC_KP; ++kp) {
+            const float4 acs[2] = {umma::lds_f4(al + kp * 512), umma::lds_f4(al + kp * 512 + 64)};
+            const float2 wos[2] = {umma::lds_f2(wout_a + (kp * 64 + cq * DEC_CW + 2 * lc) * 4),
+                                   umma::lds_f2(wout_a + (kp * 64 + cq * DEC_CW + 8 + 2 * lc) * 4)};
+            umma::tc_wait_ld();
+            if (kp + 1 < DEC_KP) {
+              umma::tmem_ld_16x256b_x2(src + (kp + 1) * 64, v[(kp + 1) & 1][0]);
+              umma::tmem_ld_16x256b_x2(src + (16u << 16) + (kp + 1) * 64, v[(kp + 1) & 1][1]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float x0 = __uint_as_float(v[j >> 1][4 * i + 2 * (j & 1)]);
-                const float x1 = __uint_as_float(v[j >> 1][4 * i + 2 * (j & 1) + 1]);
-                part[j] = fmaf(fmaxf(fmaf(x0, ac.x, ac.z), 0.f), wo.x, part[j]);
-                part[j] = fmaf(fmaxf(fmaf(x1, ac.y, ac.w), 0.f), wo.y, part[j]);
+                const float x0 = __uint_as_float(v[kp & 1][j >> 1][4 * i + 2 * (j & 1)]);
+                const float x1 = __uint_as_float(v[kp & 1][j >> 1][4 * i + 2 * (j & 1) + 1]);
+                part[j] = fmaf(fmaxf(fmaf(x0, acs[i].x, acs[i].z), 0.f), wos[i].x, part[j]);
+                part[j] = fmaf(fmaxf(fmaf(x1, acs[i].y, acs[i].w), 0.f), wos[i].y, part[j]);
               }
             }
           }
@@ -288,21 +290,21 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
           for (int j = 0; j < 4; ++j) {
             part[j] += __shfl_xor_sync(0xffffffffu, part[j], 1);
             part[j] += __shfl_xor_sync(0xffffffffu, part[j], 2);
-            if (lc == 0) s_out[hsel * DEC_TILE_M + q * 32 + lr + 8 * j] = part[j];
+            if (lc == 0) s_out[cq * DEC_TILE_M + q * 32 + lr + 8 * j] = part[j];
           }
           umma::tc_fence_before();
-          asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
-          if (hsel == 0 && lc == 0) {
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * DEC_EPI_WARPS) : "memory");  // the epilogue warps only
+          if (cq == 0 && lc == 0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int t = t0 + 8 * j, rr = q * 32 + lr + 8 * j;
-              if (t < T) logits[(size_t)obj * T + t] = (s_out[rr] + s_out[DEC_TILE_M + rr]) + fc_out_b;
+              if (t < T)
+                logits[(size_t)obj * T + t] =
+                    ((s_out[rr] + s_out[DEC_TILE_M + rr]) + (s_out[2 * DEC_TILE_M + rr] + s_out[3 * DEC_TILE_M + rr])) + fc_out_b;
             }
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&bars->aff_empty[ab]);
     }
   }
   umma::tc_fence_before();
