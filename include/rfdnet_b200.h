@@ -108,6 +108,19 @@ int rfd_pointwise_mlp_f32(const float *x, const float *W, const float *scale, co
                           const float *residual, int relu, int pool, int B, int Cin, int Cout, int L, float *y,
                           void *stream);
 
+/* ---- (a6) grouped shared-MLP + max over nsample on tcgen05 tensor cores (bf16 operands, fp32 accumulate; eval mode).
+ * Replaces the three Conv2d(1x1)+BN2d+ReLU and the max_pool2d of PointnetSAModuleVotes.forward
+ * (../pointnet2_modules.py:9-19,237-243) for one SA layer in one kernel.
+ *   pack (once per checkpoint): W_l (C_l, C_{l-1}) f32 row-major, BN scale_l (C_l) folded into the bf16 weights
+ *     -> packed (rfd_sa_mlp_tc_packed_bytes bytes, 0 = unsupported widths);
+ *   run: x (B, Ct, M, S) f32 grouped tensor, shift (C1+C2+C3) f32 -> out (B, C3, M) f32 = max_s relu(...).
+ * Supported: Ct <= 320; C1, C2 in {64,128}; C3 in {64,128,192,256}; S in {16,32,64,128}. */
+size_t rfd_sa_mlp_tc_packed_bytes(int Ct, int C1, int C2, int C3);
+int rfd_sa_mlp_tc_pack(const float *W1, const float *scale1, const float *W2, const float *scale2, const float *W3,
+                       const float *scale3, int Ct, int C1, int C2, int C3, void *packed, void *stream);
+int rfd_sa_mlp_tc(const float *x, int B, int Ct, int M, int S, const void *packed, const float *shift, int C1, int C2,
+                  int C3, float *out, void *stream);
+
 /* ---- (a13) occupancy query lattice: out (R^3,3) f32 = box_size * linspace(-0.5,0.5,R) on each axis, z fastest */
 int rfd_make_3d_grid(int R, float box_size, float *out, void *stream);
 

@@ -30,6 +30,9 @@ SIGNATURES = {
     "rfd_three_nn_interpolate": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "rfd_pointwise_mlp_f32": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "rfd_make_3d_grid": [_i, _f, _vp, _vp],
+    "rfd_sa_mlp_tc_packed_bytes": [_i, _i, _i, _i],
+    "rfd_sa_mlp_tc_pack": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "rfd_sa_mlp_tc": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
     "rfd_onet_packed_bytes": [_i],
     "rfd_onet_pack_weights": [_vp, _i, _vp, _vp],
     "rfd_onet_aff_floats": [],
@@ -39,7 +42,7 @@ SIGNATURES = {
     "rfd_umma_selftest": [_vp, _vp, _vp, _vp],
 }
 _RESTYPES = {"rfd_status_string": ctypes.c_char_p, "rfd_last_error": ctypes.c_char_p,
-             "rfd_launch_count": _ll, "rfd_onet_packed_bytes": _sz, "rfd_onet_aff_floats": _sz}
+             "rfd_launch_count": _ll, "rfd_onet_packed_bytes": _sz, "rfd_onet_aff_floats": _sz, "rfd_sa_mlp_tc_packed_bytes": _sz}
 
 _lib = None
 

@@ -20,9 +20,13 @@
 //     (rfd_onet_cbn_tables).  The epilogue warps read the accumulator with tcgen05.ld, apply that affine + ReLU,
 //     round to bf16 and write the next layer's A operand into shared memory in the UMMA K-major 128B-swizzled
 //     layout, 64-channel panel by panel; the MMA of the next layer starts on a panel as soon as it is complete;
-//   * weights (10 x 256 x 256 bf16, pre-swizzled by rfd_onet_pack_weights) stream from L2 through a 3-stage ring
-//     of 32-KB bulk copies (cp.async.bulk, mbarrier complete_tx) issued by a dedicated producer warp, which also
-//     prefetches the next tile's affine table;
+//   * weights (10 x 256 x 256 bf16, pre-swizzled by rfd_onet_pack_weights) stream from L2 through a 4-stage ring
+//     of 32-KB bulk copies (cp.async.bulk, mbarrier complete_tx) issued by a dedicated producer warp; each CTA owns a
+//     contiguous chunk of tiles, so the per-object affine table is reloaded only when the object changes;
+//   * tried and rejected (profiles/r1_decoder_history.md): issuing each layer as two N=128 halves so that the
+//     epilogue of the first half hides behind the MMAs of the second -- the A panels would have to be double
+//     buffered (WAR hazard on the in-place activation panels) and the N=128 MMAs re-read A twice, which made the
+//     kernel shared-memory bound (13.7 ms vs 8.7 ms for 256 objects);
 //   * fc_p (K = 3) and fc_out (N = 1) are evaluated in fp32 on the CUDA cores inside the same kernel.
 #include "common.cuh"
 #include "umma.cuh"

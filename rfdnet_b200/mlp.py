@@ -64,3 +64,36 @@ def run_mlp(x, layers, pool_last=1):
         last = li == len(layers) - 1
         x = pointwise_layer(x, W, s, t, relu, pool=pool_last if last else 1)
     return x
+
+
+class PackedMlp3:
+    """bf16 tensor-core weights of a 3-layer shared MLP (rfd_sa_mlp_tc_pack); None if the widths are unsupported."""
+
+    def __init__(self, layers):
+        (W1, s1, t1, r1), (W2, s2, t2, r2), (W3, s3, t3, r3) = layers
+        assert r1 and r2 and r3
+        self.Ct, self.C1, self.C2, self.C3 = W1.shape[1], W1.shape[0], W2.shape[0], W3.shape[0]
+        lib = _lib.load()
+        nbytes = lib.rfd_sa_mlp_tc_packed_bytes(self.Ct, self.C1, self.C2, self.C3)
+        self.ok = nbytes > 0
+        if not self.ok:
+            return
+        dev = W1.device
+        self.packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.shift = torch.cat([t1, t2, t3]).contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(lib.rfd_sa_mlp_tc_pack(W1.data_ptr(), s1.data_ptr(), W2.data_ptr(), s2.data_ptr(), W3.data_ptr(),
+                                              s3.data_ptr(), self.Ct, self.C1, self.C2, self.C3, self.packed.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream), "sa_mlp_tc_pack")
+
+    def __call__(self, grouped):
+        """grouped (B, Ct, M, S) f32 -> (B, C3, M) f32."""
+        B, Ct, M, S = grouped.shape
+        assert Ct == self.Ct
+        out = torch.empty((B, self.C3, M), dtype=torch.float32, device=grouped.device)
+        flop = 2.0 * B * M * S * (self.Ct * self.C1 + self.C1 * self.C2 + self.C2 * self.C3)
+        with torch.cuda.device(grouped.device), _lib.timed("sa_mlp_tc", flop):
+            _lib.check(_lib.load().rfd_sa_mlp_tc(grouped.data_ptr(), B, Ct, M, S, self.packed.data_ptr(),
+                                                 self.shift.data_ptr(), self.C1, self.C2, self.C3, out.data_ptr(),
+                                                 torch.cuda.current_stream().cuda_stream), "sa_mlp_tc")
+        return out

@@ -35,16 +35,20 @@ class _FoldCache:
             self._fold = _mlp.fold_sequential(seq)
         return self._fold
 
-    def train(self, mode=True):
+    def _drop(self):
         self._fold = None
+        self._tc = None
+
+    def train(self, mode=True):
+        self._drop()
         return super().train(mode)
 
     def _load_from_state_dict(self, *a, **k):
-        self._fold = None
+        self._drop()
         return super()._load_from_state_dict(*a, **k)
 
     def _apply(self, fn, *a, **k):
-        self._fold = None
+        self._drop()
         return super()._apply(fn, *a, **k)
 
 
@@ -53,8 +57,10 @@ class PointnetSAModuleVotes(_FoldCache, nn.Module):
 
     def __init__(self, *, mlp: List[int], npoint: int = None, radius: float = None, nsample: int = None,
                  bn: bool = True, use_xyz: bool = True, pooling: str = 'max', sigma: float = None,
-                 normalize_xyz: bool = False, sample_uniformly: bool = False, ret_unique_cnt: bool = False):
+                 normalize_xyz: bool = False, sample_uniformly: bool = False, ret_unique_cnt: bool = False,
+                 precision: str = 'fp32'):
         super().__init__()
+        self.precision = precision  # 'fp32' (exact CUDA-core path) | 'bf16' (tcgen05 shared-MLP, eval only)
         self.npoint, self.radius, self.nsample = npoint, radius, nsample
         self.pooling = pooling
         self.use_xyz = use_xyz
@@ -98,8 +104,14 @@ class PointnetSAModuleVotes(_FoldCache, nn.Module):
             xyz, new_xyz, None if features is None else features.contiguous(), self.radius, self.nsample,
             self.use_xyz, self.normalize_xyz)
         Ct = grouped.shape[1]
+        layers = self._folded(self.mlp_module)
+        if self.precision == 'bf16' and len(layers) == 3 and self.nsample in (16, 32, 64):
+            if getattr(self, "_tc", None) is None:
+                self._tc = _mlp.PackedMlp3(layers)
+            if self._tc.ok:
+                return new_xyz, self._tc(grouped), inds
         x = grouped.view(B, Ct, self.npoint * self.nsample)
-        new_features = _mlp.run_mlp(x, self._folded(self.mlp_module), pool_last=self.nsample)
+        new_features = _mlp.run_mlp(x, layers, pool_last=self.nsample)
         return new_xyz, new_features, inds
 
     # -- training / generic: the reference's sequence (:219-260) on the drop-in ops

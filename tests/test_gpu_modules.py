@@ -89,3 +89,51 @@ def test_detection_80k_batch_shapes_and_determinism():
     for k in ("sa1_inds", "fp2_features", "center", "sem_cls_scores"):
         assert torch.equal(ep[k], ep2[k]), k  # no atomics on the forward path: bitwise reproducible
     assert torch.isfinite(ep["center"]).all()
+
+
+@pytest.mark.parametrize("Ct,C1,C2,C3,M,S", [(4, 64, 64, 128, 2048, 64), (131, 128, 128, 256, 1024, 32),
+                                             (259, 128, 128, 256, 512, 16), (259, 128, 128, 128, 256, 16),
+                                             (259, 128, 128, 128, 100, 16), (20, 64, 128, 192, 37, 32)])
+def test_sa_shared_mlp_tensor_core_vs_fp32(Ct, C1, C2, C3, M, S):
+    """tcgen05 grouped MLP + max (bf16 operands, fp32 accumulate) against the exact fp32 CUDA-core path."""
+    from rfdnet_b200 import mlp
+    seq = pointnet2_modules.build_shared_mlp([Ct, C1, C2, C3]).eval()
+    seeded_fill(seq, Ct + C3)
+    seq = seq.to(DEV)
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(2, Ct, M, S, generator=g).to(DEV)
+    layers = mlp.fold_sequential(seq)
+    ref = mlp.run_mlp(x.view(2, Ct, M * S), layers, pool_last=S)
+    tc = mlp.PackedMlp3(layers)
+    assert tc.ok
+    out = tc(x)
+    assert out.shape == (2, C3, M)
+    scale = float(ref.abs().max())
+    err = float((out - ref).abs().max())
+    print(f"sa_mlp_tc Ct={Ct} S={S}: max|err| {err:.3e} scale {scale:.3f}")
+    assert err <= 2e-2 * max(1.0, scale)
+    # and against torch in fp32 (the reference's own module sequence, TF32 off)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            t = torch.nn.functional.max_pool2d(seq(x), kernel_size=[1, S]).squeeze(-1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert torch.allclose(ref, t, atol=1e-4, rtol=1e-4)
+
+
+def test_detection_bf16_sa_path_close_to_fp32():
+    net = detection.DetectionHotPath(1, 256).eval()
+    seeded_fill(net, 5)
+    net = net.to(DEV)
+    pc = torch.from_numpy(scannet_like_batch(1, 80000, seed0=9)).to(DEV)
+    with torch.no_grad():
+        ep, _ = net(pc)
+        for m in net.modules():
+            if isinstance(m, pointnet2_modules.PointnetSAModuleVotes):
+                m.precision = 'bf16'
+        ep_b, _ = net(pc)
+    assert torch.equal(ep["sa1_inds"], ep_b["sa1_inds"])
+    f, fb = ep["sa1_features"], ep_b["sa1_features"]
+    assert float((f - fb).abs().max()) <= 3e-2 * max(1.0, float(f.abs().max()))
