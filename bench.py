@@ -81,10 +81,10 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_model(device, seed=0):
+def build_model(device, seed=0, backbone_precision="fp32"):
     from rfdnet_b200.pipeline import SceneHotPath
     from rfdnet_b200.synth import seeded_fill
-    net = SceneHotPath().eval()
+    net = SceneHotPath(backbone_precision=backbone_precision).eval()
     seeded_fill(net, seed)
     return net.to(device)
 
@@ -157,7 +157,7 @@ def run_gpu(args, rank, world, local):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     S = args.scenes
-    net = build_model(dev)
+    net = build_model(dev, backbone_precision=args.backbone_precision)
     sets = [make_inputs(S, 1000 * rank + 100 * i) for i in range(2)]  # two rotating input sets
     dev_sets = [(pc.to(dev), codes.to(dev)) for pc, codes in sets]
     host_sets = [(pc.pin_memory(), codes.pin_memory()) for pc, codes in sets]
@@ -217,6 +217,8 @@ def run_gpu(args, rank, world, local):
     dec_ms = float(np.mean([t for t, _ in dec]))
     dec_tflops = float(np.mean([w for _, w in dec])) / (dec_ms * 1e-3) / 1e12
     qg_gbs = sum(w for _, w in qg) / (sum(t for t, _ in qg) * 1e-3) / 1e9
+    satc = [(s.elapsed_time(e), w) for n, s, e, w in timers if n == "sa_mlp_tc"]
+    satc_tflops = (sum(w for _, w in satc) / (sum(t for t, _ in satc) * 1e-3) / 1e12) if satc else None
     value = world * S * args.steps / (ms_max * 1e-3)
     e2e = world * S * args.steps / t_e2e
 
@@ -241,8 +243,8 @@ def run_gpu(args, rank, world, local):
         "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "full hot path: 80k-pt scene -> backbone(4 SA+2 FP, fp32)+vote+256 proposals -> ONet "
-                               "decoder 256 x 32^3 (bf16 tcgen05, fp32 accumulate)",
+        "config": {"workload": "full hot path: 80k-pt scene -> backbone(4 SA+2 FP, %s)+vote+256 proposals (vote-agg MLP bf16 "
+                               "tcgen05) -> ONet decoder 256 x 32^3 (bf16 tcgen05, fp32 accumulate)" % args.backbone_precision,
                    "scenes_per_gpu_per_step": S, "points": 80000, "proposals": 256, "grid": 32,
                    "parallelism": f"dp{world} (scenes sharded, no collective)",
                    "l2": "per-step working set (logits %d MB + clouds) exceeds the 126 MB L2; inputs rotate over 2 sets"
@@ -254,6 +256,9 @@ def run_gpu(args, rank, world, local):
         "ballquery_group": {"achieved": qg_gbs, "peak": hbm, "unit": "GB/s", "frac": qg_gbs / hbm,
                             "launches_per_step": len(qg) // args.steps, "bound": "hbm",
                             "ms_per_step": sum(t for t, _ in qg) / args.steps},
+        "sa_mlp_tc": {"achieved": satc_tflops, "unit": "TFLOP/s", "launches_per_step": len(satc) // args.steps,
+                      "ms_per_step": sum(t for t, _ in satc) / args.steps if satc else None,
+                      "layers": "vote-aggregation SA (config 3)" + (" + SA1-4" if args.backbone_precision == "bf16" else "")},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": t_e2e / args.steps * 1e3},
@@ -271,6 +276,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=4, help="scenes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--backbone-precision", default="fp32", choices=["fp32", "bf16"],
+                    help="shared MLPs of SA1-4: fp32 CUDA cores (BASELINE config 2, default) or bf16 tcgen05")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))

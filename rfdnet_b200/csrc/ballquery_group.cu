@@ -51,9 +51,194 @@ __device__ __forceinline__ int ball_scan(const float *__restrict__ xyz, int n, f
   return cnt < nsample ? cnt : nsample;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Uniform-grid candidate search for large clouds (SA1: N = 80000, 2048 queries -> 164 M brute-force pair tests).
+// Points are binned into cells of edge >= 1.001 * radius, so every point within `radius` of a query lies in the
+// 3x3x3 cell neighbourhood of the query's cell.  The hit PREDICATE is unchanged (same fp32 arithmetic as the
+// reference), only the candidate set shrinks; the reference's "first nsample hits by ascending index" order is
+// restored by ranking the collected hits by index (rank = number of hits with a smaller index), so the output is
+// bit-identical to the brute-force scan.  A query with more than GRID_CAP hits falls back to the brute-force scan.
+constexpr int GRID_G = 32;                        // max cells per axis
+constexpr int GRID_NC = GRID_G * GRID_G * GRID_G;  // 32768
+constexpr int GRID_CAP = 512;                      // hits kept per query before falling back
+constexpr int GRID_MIN_N = 8192;                   // use the grid from this cloud size on
+
+struct GridScene {
+  float ox, oy, oz, inv_cell;
+  int gx, gy, gz, pad;
+};
+
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void grid_init_kernel(int *bbox, int B) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < B * 6) bbox[e] = (e % 6) < 3 ? 0x7fffffff : (int)0x80000000;
+}
+
+__global__ void __launch_bounds__(256) grid_bbox_kernel(const float *__restrict__ xyz, int n, int *__restrict__ bbox) {
+  const int b = blockIdx.y;
+  const float *p = xyz + (size_t)b * n * 3;
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __ldg(p + (size_t)k * 3 + c);
+      if (v == v) { mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v); }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], off));
+      mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(bbox + b * 6 + c, f2ord(mn[c]));
+      atomicMax(bbox + b * 6 + 3 + c, f2ord(mx[c]));
+    }
+  }
+}
+
+__global__ void grid_setup_kernel(const int *__restrict__ bbox, float radius, int B, GridScene *__restrict__ gs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float mn[3], ext[3], emax = 0.f;
+  for (int c = 0; c < 3; ++c) {
+    mn[c] = ord2f(bbox[b * 6 + c]);
+    const float mx = ord2f(bbox[b * 6 + 3 + c]);
+    ext[c] = (mx >= mn[c]) ? mx - mn[c] : 0.f;
+    if (!(ext[c] < 3.0e38f)) ext[c] = 3.0e38f;
+    emax = fmaxf(emax, ext[c]);
+  }
+  float cell = fmaxf(radius * 1.001f, emax / (float)(GRID_G - 1) * 1.0001f);
+  if (!(cell > 0.f)) cell = 1.f;
+  GridScene g;
+  g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
+  g.inv_cell = 1.0f / cell;
+  g.gx = min(GRID_G, (int)(ext[0] * g.inv_cell) + 1);
+  g.gy = min(GRID_G, (int)(ext[1] * g.inv_cell) + 1);
+  g.gz = min(GRID_G, (int)(ext[2] * g.inv_cell) + 1);
+  g.pad = 0;
+  gs[b] = g;
+}
+
+// integer cell coordinate along one axis, clamped to [-2, g+1] before the float->int conversion
+__device__ __forceinline__ int grid_coord(float v, float o, float inv, int g) {
+  float t = floorf((v - o) * inv);
+  t = fminf(fmaxf(t, -2.f), (float)(g + 1));
+  return (t == t) ? (int)t : 0;
+}
+
+__global__ void __launch_bounds__(256)
+grid_count_kernel(const float *__restrict__ xyz, int n, const GridScene *__restrict__ gs, int *__restrict__ cellid,
+                  int *__restrict__ count) {
+  const int b = blockIdx.y;
+  const GridScene g = gs[b];
+  const float *p = xyz + (size_t)b * n * 3;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int cx = min(max(grid_coord(__ldg(p + (size_t)k * 3 + 0), g.ox, g.inv_cell, g.gx), 0), g.gx - 1);
+    const int cy = min(max(grid_coord(__ldg(p + (size_t)k * 3 + 1), g.oy, g.inv_cell, g.gy), 0), g.gy - 1);
+    const int cz = min(max(grid_coord(__ldg(p + (size_t)k * 3 + 2), g.oz, g.inv_cell, g.gz), 0), g.gz - 1);
+    const int c = (cx * g.gy + cy) * g.gz + cz;
+    cellid[(size_t)b * n + k] = c;
+    atomicAdd(count + (size_t)b * (GRID_NC + 1) + c, 1);
+  }
+}
+
+// exclusive scan of the GRID_NC counts of one scene (in place: count -> start), one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) grid_scan_kernel(int *__restrict__ count) {
+  __shared__ int s_part[1024];
+  int *c = count + (size_t)blockIdx.x * (GRID_NC + 1);
+  constexpr int PER = GRID_NC / 1024;
+  int loc[PER];
+  int sum = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { loc[i] = c[threadIdx.x * PER + i]; sum += loc[i]; }
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0;
+    __syncthreads();
+    s_part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = s_part[threadIdx.x] - sum;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { c[threadIdx.x * PER + i] = run; run += loc[i]; }
+  if (threadIdx.x == 1023) c[GRID_NC] = run;
+}
+
+__global__ void __launch_bounds__(256)
+grid_scatter_kernel(int n, const int *__restrict__ cellid, const int *__restrict__ start, int *__restrict__ fill,
+                    int *__restrict__ ids) {
+  const int b = blockIdx.y;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int c = cellid[(size_t)b * n + k];
+    const int pos = atomicAdd(fill + (size_t)b * GRID_NC + c, 1);
+    ids[(size_t)b * n + start[(size_t)b * (GRID_NC + 1) + c] + pos] = k;
+  }
+}
+
+// Grid scan for one query by one warp: collects the hits of the 27 neighbouring cells in `hits` (shared, GRID_CAP
+// ints), ranks them by index and writes the first nsample into row[] in ascending index order.
+// Returns the hit count capped at nsample, or -1 if more than GRID_CAP hits were found (caller falls back).
+__device__ __forceinline__ int ball_scan_grid(const float *__restrict__ xyz, const GridScene &g,
+                                              const int *__restrict__ start, const int *__restrict__ ids, float qx,
+                                              float qy, float qz, float radius2, int nsample, int lane, int *hits,
+                                              int *row, int &first) {
+  const int cx = grid_coord(qx, g.ox, g.inv_cell, g.gx), cy = grid_coord(qy, g.oy, g.inv_cell, g.gy),
+            cz = grid_coord(qz, g.oz, g.inv_cell, g.gz);
+  int H = 0;
+  for (int ix = max(cx - 1, 0); ix <= min(cx + 1, g.gx - 1); ++ix)
+    for (int iy = max(cy - 1, 0); iy <= min(cy + 1, g.gy - 1); ++iy) {
+      // cells (ix, iy, z0..z1) are contiguous in the cell order => one contiguous id range
+      const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.gz - 1);
+      if (z0 > z1) continue;
+      const int c0 = (ix * g.gy + iy) * g.gz;
+      const int beg = __ldg(start + c0 + z0), end = __ldg(start + c0 + z1 + 1);
+      for (int base = beg; base < end; base += 32) {
+        const int e = base + lane;
+        bool hit = false;
+        int k = 0;
+        if (e < end) {
+          k = __ldg(ids + e);
+          const float x = __ldg(xyz + (size_t)k * 3 + 0), y = __ldg(xyz + (size_t)k * 3 + 1),
+                      z = __ldg(xyz + (size_t)k * 3 + 2);
+          hit = sqdist_yxz(qx - x, qy - y, qz - z) < radius2;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask) {
+          const int pos = H + __popc(mask & ((1u << lane) - 1u));
+          if (hit && pos < GRID_CAP) hits[pos] = k;
+          H += __popc(mask);
+        }
+      }
+    }
+  if (H > GRID_CAP) return -1;
+  __syncwarp();
+  int mn = 0x7fffffff;
+  for (int h = lane; h < H; h += 32) {
+    const int id = hits[h];
+    int rank = 0;
+    for (int t = 0; t < H; ++t) rank += (hits[t] < id);
+    if (rank < nsample) row[rank] = id;
+    mn = min(mn, id);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+  first = H ? mn : 0;
+  __syncwarp();
+  return H < nsample ? H : nsample;
+}
+
 __global__ void __launch_bounds__(BQ_THREADS)
 ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int n, int m, float radius,
-                  int nsample, int *__restrict__ idx) {
+                  int nsample, int *__restrict__ idx, const GridScene *__restrict__ gs, const int *__restrict__ gstart,
+                  const int *__restrict__ gids) {
+  __shared__ int s_hits[BQ_WARPS][GRID_CAP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int j = blockIdx.x * BQ_WARPS + warp;
@@ -63,9 +248,12 @@ ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
   int *row = idx + ((size_t)b * m + j) * nsample;
   const float radius2 = __fmul_rn(radius, radius);  // reference :22
   const float qx = __ldg(new_xyz + j * 3 + 0), qy = __ldg(new_xyz + j * 3 + 1), qz = __ldg(new_xyz + j * 3 + 2);
-  int first;
-  const int cnt = ball_scan(xyz, n, qx, qy, qz, radius2, nsample, lane, first,
-                            [&](int pos, int k) { row[pos] = k; });
+  int first, cnt = -1;
+  if (gs)
+    cnt = ball_scan_grid(xyz, gs[b], gstart + (size_t)b * (GRID_NC + 1), gids + (size_t)b * n, qx, qy, qz, radius2,
+                         nsample, lane, s_hits[warp], row, first);
+  if (cnt < 0)
+    cnt = ball_scan(xyz, n, qx, qy, qz, radius2, nsample, lane, first, [&](int pos, int k) { row[pos] = k; });
   // reference :35-39: the first hit pre-fills every slot; no hit at all leaves the zero-initialised row
   const int fill = cnt == 0 ? 0 : first;
   for (int l = cnt + lane; l < nsample; l += 32) row[l] = fill;
@@ -76,8 +264,10 @@ __global__ void __launch_bounds__(BQ_THREADS)
 query_and_group_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz,
                        const float *__restrict__ features, int n, int m, int C, float radius, int nsample,
                        int use_xyz, int normalize_xyz, float *__restrict__ new_features,
-                       float *__restrict__ grouped_xyz, int *__restrict__ idx_out) {
+                       float *__restrict__ grouped_xyz, int *__restrict__ idx_out, const GridScene *__restrict__ gs,
+                       const int *__restrict__ gstart, const int *__restrict__ gids) {
   __shared__ int s_idx[BQ_WARPS][QG_MAX_S];
+  __shared__ int s_hits[BQ_WARPS][GRID_CAP];
   __shared__ float s_q[BQ_WARPS][3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
@@ -89,10 +279,13 @@ query_and_group_kernel(const float *__restrict__ xyz, const float *__restrict__ 
   if (j < m) {
     const float qx = __ldg(new_xyz + j * 3 + 0), qy = __ldg(new_xyz + j * 3 + 1), qz = __ldg(new_xyz + j * 3 + 2);
     if (lane == 0) { s_q[warp][0] = qx; s_q[warp][1] = qy; s_q[warp][2] = qz; }
-    int first;
+    int first, cnt = -1;
     int *row = s_idx[warp];
-    const int cnt = ball_scan(xyz, n, qx, qy, qz, radius2, nsample, lane, first,
-                              [&](int pos, int k) { row[pos] = k; });
+    if (gs)
+      cnt = ball_scan_grid(xyz, gs[b], gstart + (size_t)b * (GRID_NC + 1), gids + (size_t)b * n, qx, qy, qz, radius2,
+                           nsample, lane, s_hits[warp], row, first);
+    if (cnt < 0)
+      cnt = ball_scan(xyz, n, qx, qy, qz, radius2, nsample, lane, first, [&](int pos, int k) { row[pos] = k; });
     const int fill = cnt == 0 ? 0 : first;
     for (int l = cnt + lane; l < nsample; l += 32) row[l] = fill;
   }
@@ -172,6 +365,54 @@ static int launch_group(bool grad, const float *src, const int *idx, int B, int 
   return RFD_OK;
 }
 
+// builds the per-scene grids in a stream-ordered workspace; *ws must be released with grid_release()
+struct GridWs {
+  void *base = nullptr;
+  GridScene *gs = nullptr;
+  int *start = nullptr, *ids = nullptr;
+};
+
+static int grid_build(const float *xyz, int B, int N, float radius, cudaStream_t st, GridWs *w) {
+  const size_t n_gs = sizeof(GridScene) * (size_t)B;
+  const size_t n_bbox = sizeof(int) * 6 * (size_t)B;
+  const size_t n_start = sizeof(int) * (size_t)B * (GRID_NC + 1);
+  const size_t n_fill = sizeof(int) * (size_t)B * GRID_NC;
+  const size_t n_ids = sizeof(int) * (size_t)B * N;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t total = al(n_gs) + al(n_bbox) + al(n_start) + al(n_fill) + 2 * al(n_ids);
+  RFD_CHECK_CUDA(cudaMallocAsync(&w->base, total, st), "grid workspace");
+  uint8_t *p = reinterpret_cast<uint8_t *>(w->base);
+  w->gs = reinterpret_cast<GridScene *>(p); p += al(n_gs);
+  int *bbox = reinterpret_cast<int *>(p); p += al(n_bbox);
+  w->start = reinterpret_cast<int *>(p); p += al(n_start);
+  int *fill = reinterpret_cast<int *>(p); p += al(n_fill);
+  w->ids = reinterpret_cast<int *>(p); p += al(n_ids);
+  int *cellid = reinterpret_cast<int *>(p);
+  RFD_CHECK_CUDA(cudaMemsetAsync(w->start, 0, al(n_start) + al(n_fill), st), "grid memset");
+  grid_init_kernel<<<h_ceil_div(B * 6, 128), 128, 0, st>>>(bbox, B);
+  RFD_CHECK_LAUNCH("grid_init_kernel");
+  int gx = h_ceil_div(N, 256 * 8);
+  if (gx > 64) gx = 64;
+  grid_bbox_kernel<<<dim3(gx, B), 256, 0, st>>>(xyz, N, bbox);
+  RFD_CHECK_LAUNCH("grid_bbox_kernel");
+  grid_setup_kernel<<<h_ceil_div(B, 64), 64, 0, st>>>(bbox, radius, B, w->gs);
+  RFD_CHECK_LAUNCH("grid_setup_kernel");
+  int gc = h_ceil_div(N, 256 * 2);
+  if (gc > 256) gc = 256;
+  grid_count_kernel<<<dim3(gc, B), 256, 0, st>>>(xyz, N, w->gs, cellid, w->start);
+  RFD_CHECK_LAUNCH("grid_count_kernel");
+  grid_scan_kernel<<<B, 1024, 0, st>>>(w->start);
+  RFD_CHECK_LAUNCH("grid_scan_kernel");
+  grid_scatter_kernel<<<dim3(gc, B), 256, 0, st>>>(N, cellid, w->start, fill, w->ids);
+  RFD_CHECK_LAUNCH("grid_scatter_kernel");
+  return RFD_OK;
+}
+
+static void grid_release(GridWs *w, cudaStream_t st) {
+  if (w->base) (void)cudaFreeAsync(w->base, st);
+  w->base = nullptr;
+}
+
 }  // namespace rfd
 
 using namespace rfd;
@@ -183,7 +424,14 @@ extern "C" int rfd_ball_query(const float *new_xyz, const float *xyz, int B, int
   if (!new_xyz || !xyz || !idx) return RFD_ERR_INVALID_ARGUMENT;
   if (B > 65535) return RFD_ERR_UNSUPPORTED_SIZE;
   dim3 grid(h_ceil_div(M, BQ_WARPS), B);
-  ball_query_kernel<<<grid, BQ_THREADS, 0, as_stream(stream)>>>(new_xyz, xyz, N, M, radius, nsample, idx);
+  cudaStream_t st = as_stream(stream);
+  GridWs w;
+  if (N >= GRID_MIN_N && radius > 0.f) {
+    const int rc = grid_build(xyz, B, N, radius, st, &w);
+    if (rc != RFD_OK) { grid_release(&w, st); return rc; }
+  }
+  ball_query_kernel<<<grid, BQ_THREADS, 0, st>>>(new_xyz, xyz, N, M, radius, nsample, idx, w.gs, w.start, w.ids);
+  grid_release(&w, st);
   RFD_CHECK_LAUNCH("ball_query_kernel");
   return RFD_OK;
 }
@@ -197,9 +445,16 @@ extern "C" int rfd_query_and_group(const float *xyz, const float *new_xyz, const
   if (!use_xyz && C == 0) return RFD_ERR_INVALID_ARGUMENT;  // pointnet2_utils.py:347-350 assert
   if (nsample > QG_MAX_S || B > 65535) return RFD_ERR_UNSUPPORTED_SIZE;
   dim3 grid(h_ceil_div(M, BQ_WARPS), B);
-  query_and_group_kernel<<<grid, BQ_THREADS, 0, as_stream(stream)>>>(xyz, new_xyz, features, N, M, C, radius,
-                                                                      nsample, use_xyz, normalize_xyz, new_features,
-                                                                      grouped_xyz, idx);
+  cudaStream_t st = as_stream(stream);
+  GridWs w;
+  if (N >= GRID_MIN_N && radius > 0.f) {
+    const int rc = grid_build(xyz, B, N, radius, st, &w);
+    if (rc != RFD_OK) { grid_release(&w, st); return rc; }
+  }
+  query_and_group_kernel<<<grid, BQ_THREADS, 0, st>>>(xyz, new_xyz, features, N, M, C, radius, nsample, use_xyz,
+                                                      normalize_xyz, new_features, grouped_xyz, idx, w.gs, w.start,
+                                                      w.ids);
+  grid_release(&w, st);
   RFD_CHECK_LAUNCH("query_and_group_kernel");
   return RFD_OK;
 }

@@ -14,9 +14,15 @@ from . import detection, onet
 
 class SceneHotPath(nn.Module):
     def __init__(self, input_feature_dim=1, num_proposal=256, z_dim=32, c_dim=512, resolution=32, box_size=1.1,
-                 precision='bf16'):
+                 precision='bf16', backbone_precision='fp32', head_precision='bf16'):
+        """precision: ONet decoder ('bf16' tcgen05 | 'fp32').  backbone_precision: shared MLPs of SA1-4
+        (BASELINE config 2: fp32).  head_precision: shared MLP of the vote-aggregation SA layer (BASELINE config 3:
+        bf16 tensor-core path)."""
         super().__init__()
         self.detection = detection.DetectionHotPath(input_feature_dim, num_proposal)
+        for name in ("sa1", "sa2", "sa3", "sa4"):
+            getattr(self.detection.backbone, name).precision = backbone_precision
+        self.detection.detection.vote_aggregation.precision = head_precision
         self.decoder = onet.DecoderCBatchNorm(dim=3, z_dim=z_dim, c_dim=c_dim, precision=precision)
         self.num_proposal, self.z_dim, self.c_dim = num_proposal, z_dim, c_dim
         self.resolution, self.box_size = resolution, box_size

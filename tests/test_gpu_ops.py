@@ -206,3 +206,27 @@ def test_fused_group_vs_reference_python_sequence(ref_ext):
         ref = torch.cat([gx, ref_ext.group_points(feats, idx)], dim=1)
         out, _, _ = pointnet2_utils.fused_query_and_group(cloud, new_xyz, feats, radius, S, True, True)
         assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("N,M,r,S", [(9000, 700, 0.15, 32), (20000, 256, 0.3, 64), (12000, 300, 0.05, 16), (30000, 64, 1.0, 128)])
+def test_ball_query_grid_path_bit_exact(N, M, r, S):
+    """N >= 8192 takes the uniform-grid candidate search; it must reproduce the brute-force semantics bit for bit:
+    queries outside the cloud's bounding box, a dense blob with > 512 hits (brute-force fallback), duplicates."""
+    rng = np.random.default_rng(N + S)
+    cloud = rng.uniform(-2, 2, (2, N, 3)).astype(np.float32)
+    cloud[:, :1500] = rng.normal(0, 0.02, (2, 1500, 3)).astype(np.float32) + 0.5   # dense blob
+    cloud[:, 2000:2100] = cloud[:, 1900:2000]                                       # duplicates
+    q = cloud[:, rng.choice(N, M, replace=False)].copy()
+    q[:, 0] = (0.5, 0.5, 0.5)          # centre of the blob: thousands of hits
+    q[:, 1] = (2.05, 0.0, 0.0)         # just outside the bounding box
+    q[:, 2] = (40.0, 40.0, 40.0)       # far outside: no hits
+    q[:, 3] = (-2.0, -2.0, -2.0)       # corner
+    got = _ext.ball_query(cu(q), cu(cloud), r, S).cpu().numpy()
+    assert np.array_equal(got, oracle.ball_query(q, cloud, r, S))
+    if S <= 128:
+        feats = rng.normal(size=(2, 6, N)).astype(np.float32)
+        out, gxyz, idx = pointnet2_utils.fused_query_and_group(cu(cloud), cu(q), cu(feats), r, S, True, True,
+                                                               ret_grouped_xyz=True, ret_idx=True)
+        rf, rg, ri = model_ref.query_and_group(torch.from_numpy(cloud), torch.from_numpy(q), torch.from_numpy(feats),
+                                               r, S, True, True, recip=True)
+        assert np.array_equal(idx.cpu().numpy(), ri.numpy()) and torch.equal(out.cpu(), rf)
