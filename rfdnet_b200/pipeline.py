@@ -46,14 +46,35 @@ class SceneHotPath(nn.Module):
         return end_points, logits
 
     @torch.no_grad()
-    def run_host(self, pc_host, codes_host, logits_host, device):
-        """End-to-end call with HOST (pinned) buffers: H2D of the inputs, the pass, D2H of the logits and of the
-        proposal scores.  Returns bytes moved (h2d, d2h).  The caller synchronises."""
+    def run_host(self, pc_host, codes_host, logits_host, device, chunks=4):
+        """End-to-end call with HOST (pinned) buffers: H2D of the clouds and shape codes, the pass, D2H of ALL logits
+        and of the proposal scores.  The decoder runs in `chunks` object chunks; the D2H copy of a finished chunk
+        overlaps the decoding of the next one on a second stream.  Returns bytes moved (h2d, d2h); the caller
+        synchronises the device (both streams are joined before returning control of the buffers)."""
+        main = torch.cuda.current_stream(device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device)
+        copy = self._copy_stream
         pc = pc_host.to(device, non_blocking=True)
         codes = codes_host.to(device, non_blocking=True)
-        ep, logits = self.forward(pc, codes)
-        logits_host.copy_(logits, non_blocking=True)
+        ep, _ = self.detection(pc)
         scores = ep['objectness_scores'].to('cpu', non_blocking=True)
+        nobj = codes.shape[0]
+        grid = self.grid(device)
+        z = torch.zeros((nobj, self.z_dim), dtype=torch.float32, device=device)
+        step = (nobj + chunks - 1) // chunks
+        keep = []
+        for lo in range(0, nobj, step):
+            hi = min(nobj, lo + step)
+            lg = self.decoder.decode(grid, z[lo:hi], codes[lo:hi].contiguous())
+            ev = torch.cuda.Event()
+            ev.record(main)
+            copy.wait_event(ev)
+            with torch.cuda.stream(copy):
+                logits_host[lo:hi].copy_(lg, non_blocking=True)
+            lg.record_stream(copy)
+            keep.append(lg)
+        main.wait_stream(copy)
         h2d = pc_host.numel() * 4 + codes_host.numel() * 4
         d2h = logits_host.numel() * 4 + scores.numel() * 4
         return h2d, d2h
