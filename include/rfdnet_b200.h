@@ -62,6 +62,9 @@ long long rfd_launch_count(void);
 /* ---- (a1) furthest point sampling: xyz (B,N,3) f32 -> idx (B,m) i32.  N <= 196608 per scene.
  * Bit-exact with the reference kernel incl. its tie-break and the |p|^2 <= 1e-3 skip rule. */
 int rfd_furthest_point_sampling(const float *xyz, int B, int N, int m, int *idx, void *stream);
+/* same, additionally emitting the sampled coordinates new_xyz (B,m,3) f32 (NULL = skip): replaces the
+ * transpose + gather_points + transpose of PointnetSAModuleVotes.forward (../pointnet2_modules.py:219-226). */
+int rfd_furthest_point_sampling_xyz(const float *xyz, int B, int N, int m, int *idx, float *new_xyz, void *stream);
 
 /* ---- (a2) gather: points (B,C,N), idx (B,M) -> out (B,C,M);  grad: grad_out (B,C,M) -> grad_points (B,C,N) */
 int rfd_gather_points(const float *points, const int *idx, int B, int C, int N, int M, float *out, void *stream);

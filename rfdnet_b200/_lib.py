@@ -18,6 +18,7 @@ SIGNATURES = {
     "rfd_device_info": [_vp, _vp, _vp],
     "rfd_launch_count": [],
     "rfd_furthest_point_sampling": [_vp, _i, _i, _i, _vp, _vp],
+    "rfd_furthest_point_sampling_xyz": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "rfd_gather_points": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "rfd_gather_points_grad": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "rfd_ball_query": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],

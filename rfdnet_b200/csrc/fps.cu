@@ -111,7 +111,8 @@ __device__ __forceinline__ FpsRec fps_pick(const FpsRec *recs, int n, int lane) 
 
 template <int PPT>
 __global__ void __launch_bounds__(FPS_THREADS, 1)
-fps_kernel(const float *__restrict__ xyz_all, int N, int m, int bs_log2, int Q, int CS, int *__restrict__ idx_all) {
+fps_kernel(const float *__restrict__ xyz_all, int N, int m, int bs_log2, int Q, int CS, int *__restrict__ idx_all,
+           float *__restrict__ new_xyz_all) {
   extern __shared__ float4 s_pts[];  // [PPT][FPS_THREADS] this CTA's points (winner looks its xyz up here)
   __shared__ FpsRec s_warp[2][FPS_WARPS];
   __shared__ FpsRec s_cta[2][FPS_MAX_CS];
@@ -155,7 +156,11 @@ fps_kernel(const float *__restrict__ xyz_all, int N, int m, int bs_log2, int Q, 
   }
   const float p0x = __ldg(xyz + 0), p0y = __ldg(xyz + 1), p0z = __ldg(xyz + 2);
   float x1 = p0x, y1 = p0y, z1 = p0z;  // old = 0
-  if (g == 0 && m > 0) idx_out[0] = 0;
+  float *__restrict__ nx_out = new_xyz_all ? new_xyz_all + (size_t)scene * m * 3 : nullptr;
+  if (g == 0 && m > 0) {
+    idx_out[0] = 0;
+    if (nx_out) { nx_out[0] = p0x; nx_out[1] = p0y; nx_out[2] = p0z; }
+  }
   uint32_t phases = 0;
   const uint32_t bs_mask = (1u << bs_log2) - 1u;
 
@@ -220,13 +225,18 @@ fps_kernel(const float *__restrict__ xyz_all, int N, int m, int bs_log2, int Q, 
     } else {
       old = r.k; x1 = r.x; y1 = r.y; z1 = r.z;
     }
-    if (g == 0) idx_out[j] = old;
+    if (g == 0) {
+      idx_out[j] = old;
+      // the sampled coordinates are already in registers: emitting them here replaces the reference's
+      // transpose + gather_points + transpose (pointnet2_modules.py:219-226) with three stores per round
+      if (nx_out) { nx_out[j * 3 + 0] = x1; nx_out[j * 3 + 1] = y1; nx_out[j * 3 + 2] = z1; }
+    }
   }
   if (CS > 1) cluster_sync_all();  // no CTA may exit while a peer can still write into its shared memory
 }
 
 template <int PPT>
-static int launch_fps(const float *xyz, int B, int N, int m, int bs_log2, int Q, int CS, int *idx,
+static int launch_fps(const float *xyz, int B, int N, int m, int bs_log2, int Q, int CS, int *idx, float *new_xyz,
                       cudaStream_t stream, bool probe_only, int *max_clusters) {
   auto kern = fps_kernel<PPT>;
   const size_t smem = (size_t)PPT * FPS_THREADS * sizeof(float4);
@@ -252,15 +262,15 @@ static int launch_fps(const float *xyz, int B, int N, int m, int bs_log2, int Q,
     *max_clusters = n;
     return RFD_OK;
   }
-  RFD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, bs_log2, Q, CS, idx), "fps launch");
+  RFD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, bs_log2, Q, CS, idx, new_xyz), "fps launch");
   RFD_CHECK_LAUNCH("fps_kernel");
   return RFD_OK;
 }
 
 static int dispatch_fps(int ppt, const float *xyz, int B, int N, int m, int bs_log2, int Q, int CS, int *idx,
-                        cudaStream_t stream, bool probe, int *maxc) {
+                        float *new_xyz, cudaStream_t stream, bool probe, int *maxc) {
 #define RFD_FPS_CASE(P) \
-  if (ppt <= P) return launch_fps<P>(xyz, B, N, m, bs_log2, Q, CS, idx, stream, probe, maxc);
+  if (ppt <= P) return launch_fps<P>(xyz, B, N, m, bs_log2, Q, CS, idx, new_xyz, stream, probe, maxc);
   RFD_FPS_CASE(1) RFD_FPS_CASE(2) RFD_FPS_CASE(3) RFD_FPS_CASE(4) RFD_FPS_CASE(6) RFD_FPS_CASE(8)
   RFD_FPS_CASE(10) RFD_FPS_CASE(12) RFD_FPS_CASE(16) RFD_FPS_CASE(20) RFD_FPS_CASE(24)
 #undef RFD_FPS_CASE
@@ -295,6 +305,11 @@ int fps_plan(int N, int B, int num_sms, int *cs_out, int *ppt_out) {
 }  // namespace rfd
 
 extern "C" int rfd_furthest_point_sampling(const float *xyz, int B, int N, int m, int *idx, void *stream) {
+  return rfd_furthest_point_sampling_xyz(xyz, B, N, m, idx, nullptr, stream);
+}
+
+extern "C" int rfd_furthest_point_sampling_xyz(const float *xyz, int B, int N, int m, int *idx, float *new_xyz,
+                                               void *stream) {
   using namespace rfd;
   if (B < 0 || N < 1 || m < 0 || (B > 0 && (!xyz || (m > 0 && !idx)))) return RFD_ERR_INVALID_ARGUMENT;
   if (B == 0 || m == 0) return RFD_OK;
@@ -312,12 +327,12 @@ extern "C" int rfd_furthest_point_sampling(const float *xyz, int B, int N, int m
   // a 16-CTA (non-portable) cluster may not be schedulable on every part/partition: fall back to 8
   while (cs > 8) {
     int maxc = 0;
-    rc = dispatch_fps(ppt, xyz, B, N, m, bs_log2, Q, cs, idx, st, true, &maxc);
+    rc = dispatch_fps(ppt, xyz, B, N, m, bs_log2, Q, cs, idx, new_xyz, st, true, &maxc);
     if (rc != RFD_OK) return rc;
     if (maxc > 0) break;
     cs /= 2;
     ppt = ((N + FPS_THREADS - 1) / FPS_THREADS + cs - 1) / cs;
     if (ppt > FPS_MAX_PPT) return RFD_ERR_UNSUPPORTED_SIZE;
   }
-  return dispatch_fps(ppt, xyz, B, N, m, bs_log2, Q, cs, idx, st, false, nullptr);
+  return dispatch_fps(ppt, xyz, B, N, m, bs_log2, Q, cs, idx, new_xyz, st, false, nullptr);
 }

@@ -64,7 +64,29 @@ class Pointnet2Backbone(nn.Module):
         return end_points
 
 
-class VotingModule(nn.Module):
+class _HeadFoldCache:
+    """folded (W, scale, shift) of conv1/bn1, conv2/bn2, conv3 -- recomputed only after the weights change"""
+
+    def _heads(self):
+        if getattr(self, "_hf", None) is None:
+            self._hf = (_mlp.fold_conv_bn(self.conv1, self.bn1), _mlp.fold_conv_bn(self.conv2, self.bn2),
+                        _mlp.fold_conv_bn(self.conv3, None))
+        return self._hf
+
+    def train(self, mode=True):
+        self._hf = None
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._hf = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._hf = None
+        return super()._apply(fn, *a, **k)
+
+
+class VotingModule(_HeadFoldCache, nn.Module):
     def __init__(self, vote_factor=1, seed_feature_dim=256):
         super().__init__()
         self.vote_factor = vote_factor
@@ -82,9 +104,10 @@ class VotingModule(nn.Module):
         fast = not self.training and not torch.is_grad_enabled() and seed_features.is_cuda
         if fast:
             x = seed_features.contiguous()
-            net = _mlp.pointwise_layer(x, *_mlp.fold_conv_bn(self.conv1, self.bn1), relu=True)
-            net = _mlp.pointwise_layer(net, *_mlp.fold_conv_bn(self.conv2, self.bn2), relu=True)
-            net = _mlp.pointwise_layer(net, *_mlp.fold_conv_bn(self.conv3, None), relu=False)
+            h1, h2, h3 = self._heads()
+            net = _mlp.pointwise_layer(x, *h1, relu=True)
+            net = _mlp.pointwise_layer(net, *h2, relu=True)
+            net = _mlp.pointwise_layer(net, *h3, relu=False)
         else:
             net = F.relu(self.bn1(self.conv1(seed_features)))
             net = F.relu(self.bn2(self.conv2(net)))
@@ -116,7 +139,7 @@ def decode_scores(net, end_points, num_heading_bin, num_size_cluster):
     return end_points
 
 
-class ProposalModule(nn.Module):
+class ProposalModule(_HeadFoldCache, nn.Module):
     def __init__(self, num_class=8, num_heading_bin=12, num_size_cluster=8, num_proposal=256,
                  sampling='vote_fps', seed_feat_dim=256):
         super().__init__()
@@ -149,9 +172,10 @@ class ProposalModule(nn.Module):
         end_points['aggregated_vote_inds'] = sample_inds
         fast = not self.training and not torch.is_grad_enabled() and features.is_cuda
         if fast:
-            net = _mlp.pointwise_layer(features.contiguous(), *_mlp.fold_conv_bn(self.conv1, self.bn1), relu=True)
-            net = _mlp.pointwise_layer(net, *_mlp.fold_conv_bn(self.conv2, self.bn2), relu=True)
-            net = _mlp.pointwise_layer(net, *_mlp.fold_conv_bn(self.conv3, None), relu=False)
+            h1, h2, h3 = self._heads()
+            net = _mlp.pointwise_layer(features.contiguous(), *h1, relu=True)
+            net = _mlp.pointwise_layer(net, *h2, relu=True)
+            net = _mlp.pointwise_layer(net, *h3, relu=False)
         else:
             net = F.relu(self.bn1(self.conv1(features)))
             net = F.relu(self.bn2(self.conv2(net)))

@@ -96,10 +96,10 @@ class PointnetSAModuleVotes(_FoldCache, nn.Module):
         xyz = xyz.contiguous()
         B, N, _ = xyz.shape
         if inds is None:
-            inds = pointnet2_utils._ext.furthest_point_sampling(xyz, self.npoint)
+            inds, new_xyz = pointnet2_utils.fps_with_xyz(xyz, self.npoint)  # coordinates come out of the FPS kernel
         else:
             assert inds.shape[1] == self.npoint
-        new_xyz = torch.gather(xyz, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3))  # exact copy of rows
+            new_xyz = pointnet2_utils._ext.gather_points(xyz.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
         grouped, _, _ = pointnet2_utils.fused_query_and_group(
             xyz, new_xyz, None if features is None else features.contiguous(), self.radius, self.nsample,
             self.use_xyz, self.normalize_xyz)

@@ -116,6 +116,18 @@ class BallQuery(Function):
 ball_query = BallQuery.apply
 
 
+def fps_with_xyz(xyz, npoint):
+    """FPS that also returns the sampled coordinates (B,npoint,3) straight from the kernel (inference path)."""
+    B, N, _ = xyz.shape
+    idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+    new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device), _lib.timed("fps", float(B) * (12.0 * N + 4.0 * npoint)):
+        _lib.check(_lib.load().rfd_furthest_point_sampling_xyz(xyz.data_ptr(), B, N, int(npoint), idx.data_ptr(),
+                                                                new_xyz.data_ptr(),
+                                                                torch.cuda.current_stream().cuda_stream), "fps")
+    return idx, new_xyz
+
+
 def fused_query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz=True, normalize_xyz=False,
                           ret_grouped_xyz=False, ret_idx=False):
     """One kernel for QueryAndGroup.forward (pointnet2_utils.py:319-344): ball query + both gathers +

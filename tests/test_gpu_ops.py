@@ -230,3 +230,13 @@ def test_ball_query_grid_path_bit_exact(N, M, r, S):
         rf, rg, ri = model_ref.query_and_group(torch.from_numpy(cloud), torch.from_numpy(q), torch.from_numpy(feats),
                                                r, S, True, True, recip=True)
         assert np.array_equal(idx.cpu().numpy(), ri.numpy()) and torch.equal(out.cpu(), rf)
+
+
+def test_fps_fused_new_xyz_output():
+    """rfd_furthest_point_sampling_xyz: the coordinates emitted by the FPS kernel are exactly the gathered rows."""
+    for cloud, m in ((tricky_cloud(4096, seed=1), 512), (scannet_like_batch(2, 30000, seed0=4)[..., :3].copy(), 700),
+                     (np.zeros((1, 64, 3), np.float32), 5)):
+        x = cu(cloud)
+        idx, new_xyz = pointnet2_utils.fps_with_xyz(x, m)
+        assert torch.equal(idx, _ext.furthest_point_sampling(x, m))
+        assert torch.equal(new_xyz, torch.gather(x, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)))
