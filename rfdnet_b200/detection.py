@@ -30,6 +30,35 @@ class Pointnet2Backbone(nn.Module):
         self.fp1 = PointnetFPModule(mlp=[256 + 256, 256, 256])
         self.fp2 = PointnetFPModule(mlp=[256 + 256, 256, 256])
 
+    def _forward_fused(self, xyz, features, end_points):
+        """Inference schedule.  The four FPS runs only depend on coordinates (SA(k+1) samples the points SA(k)
+        sampled), so the serial FPS chain of SA2-4 runs on a side stream while the main stream does SA1's ball
+        query, grouping and shared MLP -- same kernels, same results, shorter critical path."""
+        main = torch.cuda.current_stream(xyz.device)
+        if getattr(self, "_side", None) is None or self._side.device != xyz.device:
+            self._side = torch.cuda.Stream(xyz.device)
+        side = self._side
+        i1, x1 = pointnet2_utils.fps_with_xyz(xyz.contiguous(), self.sa1.npoint)
+        side.wait_stream(main)
+        x1.record_stream(side)
+        with torch.cuda.stream(side):
+            i2, x2 = pointnet2_utils.fps_with_xyz(x1, self.sa2.npoint)
+            i3, x3 = pointnet2_utils.fps_with_xyz(x2, self.sa3.npoint)
+            i4, x4 = pointnet2_utils.fps_with_xyz(x3, self.sa4.npoint)
+        _, f1, _ = self.sa1(xyz, features, i1, x1)
+        main.wait_stream(side)
+        for t in (i2, x2, i3, x3, i4, x4):
+            t.record_stream(main)
+        _, f2, _ = self.sa2(x1, f1, i2, x2)
+        _, f3, _ = self.sa3(x2, f2, i3, x3)
+        _, f4, _ = self.sa4(x3, f3, i4, x4)
+        f = self.fp1(x3, x4, f3, f4)
+        f = self.fp2(x2, x3, f2, f)
+        end_points.update(sa1_inds=i1, sa1_xyz=x1, sa1_features=f1, sa2_inds=i2, sa2_xyz=x2, sa2_features=f2,
+                          sa3_xyz=x3, sa3_features=f3, sa4_xyz=x4, sa4_features=f4, fp2_features=f, fp2_xyz=x2,
+                          fp2_inds=i1[:, 0:x2.shape[1]])
+        return end_points
+
     def _break_up_pc(self, pc):
         xyz = pc[..., 0:3].contiguous()
         features = (pc[..., 3:3 + self.input_feature_dim].transpose(1, 2).contiguous()
@@ -40,6 +69,9 @@ class Pointnet2Backbone(nn.Module):
         if not end_points:
             end_points = {}
         xyz, features = self._break_up_pc(pointcloud)
+        if (not self.training and not torch.is_grad_enabled() and xyz.is_cuda
+                and all(getattr(self, n)._fast_ok(xyz, None) for n in ("sa1", "sa2", "sa3", "sa4"))):
+            return self._forward_fused(xyz, features, end_points)
         xyz, features, fps_inds = self.sa1(xyz, features)
         end_points['sa1_inds'] = fps_inds
         end_points['sa1_xyz'] = xyz

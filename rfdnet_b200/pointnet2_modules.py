@@ -86,16 +86,20 @@ class PointnetSAModuleVotes(_FoldCache, nn.Module):
                 and self.pooling == 'max' and not self.sample_uniformly and xyz.is_cuda
                 and self.nsample in (4, 8, 16, 32, 64))
 
-    def forward(self, xyz, features=None, inds=None):
+    def forward(self, xyz, features=None, inds=None, new_xyz=None):
+        """`new_xyz` (B,npoint,3), optional and only honoured together with `inds` on the fused inference path: the
+        sampled coordinates when the caller already ran FPS (Pointnet2Backbone pre-samples SA2-4 on a side stream)."""
         if self._fast_ok(xyz, features):
-            return self._forward_fused(xyz, features, inds)
+            return self._forward_fused(xyz, features, inds, new_xyz)
         return self._forward_reference(xyz, features, inds)
 
     # -- inference: sm_100a kernels end to end
-    def _forward_fused(self, xyz, features, inds):
+    def _forward_fused(self, xyz, features, inds, new_xyz=None):
         xyz = xyz.contiguous()
         B, N, _ = xyz.shape
-        if inds is None:
+        if inds is not None and new_xyz is not None:
+            assert inds.shape[1] == self.npoint and new_xyz.shape[1] == self.npoint
+        elif inds is None:
             inds, new_xyz = pointnet2_utils.fps_with_xyz(xyz, self.npoint)  # coordinates come out of the FPS kernel
         else:
             assert inds.shape[1] == self.npoint
