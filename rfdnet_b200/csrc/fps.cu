@@ -23,13 +23,15 @@
 //     ascending k -- so the in-register strict '>' scan is already rank-ordered;
 //   * "no candidate" (all points skipped) reproduces the reference result old = 0.
 #include "common.cuh"
+#include <cmath>
+#include <cstdlib>
 
 namespace rfd {
 
-constexpr int FPS_THREADS = 512;
-constexpr int FPS_WARPS = FPS_THREADS / 32;
+constexpr int FPS_MAX_WARPS = 32;
 constexpr int FPS_MAX_CS = 16;
-constexpr int FPS_MAX_PPT = 24;
+constexpr int FPS_MAX_PPT = 24;    // 512-thread CTAs (<= 128 registers/thread)
+constexpr int FPS_MAX_PPT_1K = 8;  // 1024-thread CTAs (<= 64 registers/thread)
 
 struct __align__(16) FpsRec {
   uint32_t hi, lo;  // key: value bits, ~rank  (0,0 = no candidate)
@@ -109,11 +111,12 @@ __device__ __forceinline__ FpsRec fps_pick(const FpsRec *recs, int n, int lane) 
   return r;
 }
 
-template <int PPT>
+template <int PPT, int FPS_THREADS>
 __global__ void __launch_bounds__(FPS_THREADS, 1)
 fps_kernel(const float *__restrict__ xyz_all, int N, int m, int bs_log2, int Q, int CS, int *__restrict__ idx_all,
            float *__restrict__ new_xyz_all) {
   extern __shared__ float4 s_pts[];  // [PPT][FPS_THREADS] this CTA's points (winner looks its xyz up here)
+  constexpr int FPS_WARPS = FPS_THREADS / 32;
   __shared__ FpsRec s_warp[2][FPS_WARPS];
   __shared__ FpsRec s_cta[2][FPS_MAX_CS];
   __shared__ __align__(8) uint64_t s_mbar[2];
@@ -235,10 +238,10 @@ fps_kernel(const float *__restrict__ xyz_all, int N, int m, int bs_log2, int Q, 
   if (CS > 1) cluster_sync_all();  // no CTA may exit while a peer can still write into its shared memory
 }
 
-template <int PPT>
+template <int PPT, int FPS_THREADS>
 static int launch_fps(const float *xyz, int B, int N, int m, int bs_log2, int Q, int CS, int *idx, float *new_xyz,
                       cudaStream_t stream, bool probe_only, int *max_clusters) {
-  auto kern = fps_kernel<PPT>;
+  auto kern = fps_kernel<PPT, FPS_THREADS>;
   const size_t smem = (size_t)PPT * FPS_THREADS * sizeof(float4);
   RFD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fps attr smem");
   if (CS > 8)
@@ -267,12 +270,18 @@ static int launch_fps(const float *xyz, int B, int N, int m, int bs_log2, int Q,
   return RFD_OK;
 }
 
-static int dispatch_fps(int ppt, const float *xyz, int B, int N, int m, int bs_log2, int Q, int CS, int *idx,
-                        float *new_xyz, cudaStream_t stream, bool probe, int *maxc) {
-#define RFD_FPS_CASE(P) \
-  if (ppt <= P) return launch_fps<P>(xyz, B, N, m, bs_log2, Q, CS, idx, new_xyz, stream, probe, maxc);
-  RFD_FPS_CASE(1) RFD_FPS_CASE(2) RFD_FPS_CASE(3) RFD_FPS_CASE(4) RFD_FPS_CASE(6) RFD_FPS_CASE(8)
-  RFD_FPS_CASE(10) RFD_FPS_CASE(12) RFD_FPS_CASE(16) RFD_FPS_CASE(20) RFD_FPS_CASE(24)
+static int dispatch_fps(int threads, int ppt, const float *xyz, int B, int N, int m, int bs_log2, int Q, int CS,
+                        int *idx, float *new_xyz, cudaStream_t stream, bool probe, int *maxc) {
+#define RFD_FPS_CASE(P, T) \
+  if (ppt <= P) return launch_fps<P, T>(xyz, B, N, m, bs_log2, Q, CS, idx, new_xyz, stream, probe, maxc);
+  if (threads == 1024) {
+    RFD_FPS_CASE(1, 1024) RFD_FPS_CASE(2, 1024) RFD_FPS_CASE(3, 1024) RFD_FPS_CASE(4, 1024) RFD_FPS_CASE(5, 1024)
+    RFD_FPS_CASE(6, 1024) RFD_FPS_CASE(8, 1024)
+    return RFD_ERR_UNSUPPORTED_SIZE;
+  }
+  RFD_FPS_CASE(1, 512) RFD_FPS_CASE(2, 512) RFD_FPS_CASE(3, 512) RFD_FPS_CASE(4, 512) RFD_FPS_CASE(6, 512)
+  RFD_FPS_CASE(8, 512) RFD_FPS_CASE(10, 512) RFD_FPS_CASE(12, 512) RFD_FPS_CASE(16, 512) RFD_FPS_CASE(20, 512)
+  RFD_FPS_CASE(24, 512)
 #undef RFD_FPS_CASE
   return RFD_ERR_UNSUPPORTED_SIZE;
 }
@@ -286,17 +295,19 @@ static int ref_opt_n_threads(int work_size) {
   return v;
 }
 
-int fps_plan(int N, int B, int num_sms, int *cs_out, int *ppt_out) {
-  const int need = (N + FPS_THREADS - 1) / FPS_THREADS;  // point slots per thread column
+int fps_plan(int N, int B, int num_sms, int threads, int *cs_out, int *ppt_out) {
+  const int max_ppt = threads == 1024 ? FPS_MAX_PPT_1K : FPS_MAX_PPT;
+  const int tgt = threads == 1024 ? 5 : 10;                 // points per thread aimed for on big clouds
+  const int need = (N + threads - 1) / threads;             // point slots per thread column
   int cs = 1;
   if (N > 8192) {
-    while (cs < FPS_MAX_CS && (need + cs - 1) / cs > 10) cs *= 2;
+    while (cs < FPS_MAX_CS && (need + cs - 1) / cs > tgt) cs *= 2;
     // oversubscribed GPU: prefer fewer, fatter CTAs per scene as long as the points still fit in registers
-    while (cs > 1 && (long long)B * cs > num_sms && (need + cs / 2 - 1) / (cs / 2) <= FPS_MAX_PPT) cs /= 2;
+    while (cs > 1 && (long long)B * cs > num_sms && (need + cs / 2 - 1) / (cs / 2) <= max_ppt) cs /= 2;
   }
-  while (cs < FPS_MAX_CS && (need + cs - 1) / cs > FPS_MAX_PPT) cs *= 2;
+  while (cs < FPS_MAX_CS && (need + cs - 1) / cs > max_ppt) cs *= 2;
   const int ppt = (need + cs - 1) / cs;
-  if (ppt > FPS_MAX_PPT) return RFD_ERR_UNSUPPORTED_SIZE;
+  if (ppt > max_ppt) return RFD_ERR_UNSUPPORTED_SIZE;
   *cs_out = cs;
   *ppt_out = ppt;
   return RFD_OK;
@@ -316,8 +327,14 @@ extern "C" int rfd_furthest_point_sampling_xyz(const float *xyz, int B, int N, i
   int dev = 0, sms = 148;
   RFD_CHECK_CUDA(cudaGetDevice(&dev), "fps getdevice");
   RFD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "fps sms");
+  // CTA width: 512 threads.  1024-thread CTAs (5 points/thread, 8 warps per scheduler) were measured SLOWER on the
+  // 80k-point layer (2.28 ms vs 1.84 ms for 4 scenes): the round is bound by the reduction / exchange chain, whose
+  // cost grows with the warp count, not by the register update.  RFD_FPS_THREADS=1024 selects them for experiments.
+  int threads = 512;
+  if (const char *e = getenv("RFD_FPS_THREADS")) { const int v = atoi(e); if (v == 512 || v == 1024) threads = v; }
   int cs = 1, ppt = 1;
-  int rc = fps_plan(N, B, sms, &cs, &ppt);
+  int rc = fps_plan(N, B, sms, threads, &cs, &ppt);
+  if (rc != RFD_OK && threads == 1024) { threads = 512; rc = fps_plan(N, B, sms, threads, &cs, &ppt); }
   if (rc != RFD_OK) return rc;
   const int bs = ref_opt_n_threads(N);
   int bs_log2 = 0;
@@ -327,12 +344,17 @@ extern "C" int rfd_furthest_point_sampling_xyz(const float *xyz, int B, int N, i
   // a 16-CTA (non-portable) cluster may not be schedulable on every part/partition: fall back to 8
   while (cs > 8) {
     int maxc = 0;
-    rc = dispatch_fps(ppt, xyz, B, N, m, bs_log2, Q, cs, idx, new_xyz, st, true, &maxc);
+    rc = dispatch_fps(threads, ppt, xyz, B, N, m, bs_log2, Q, cs, idx, new_xyz, st, true, &maxc);
     if (rc != RFD_OK) return rc;
     if (maxc > 0) break;
     cs /= 2;
-    ppt = ((N + FPS_THREADS - 1) / FPS_THREADS + cs - 1) / cs;
-    if (ppt > FPS_MAX_PPT) return RFD_ERR_UNSUPPORTED_SIZE;
+    ppt = ((N + threads - 1) / threads + cs - 1) / cs;
+    if (ppt > (threads == 1024 ? FPS_MAX_PPT_1K : FPS_MAX_PPT)) {
+      if (threads == 512) return RFD_ERR_UNSUPPORTED_SIZE;
+      threads = 512;
+      ppt = ((N + threads - 1) / threads + cs - 1) / cs;
+      if (ppt > FPS_MAX_PPT) return RFD_ERR_UNSUPPORTED_SIZE;
+    }
   }
-  return dispatch_fps(ppt, xyz, B, N, m, bs_log2, Q, cs, idx, new_xyz, st, false, nullptr);
+  return dispatch_fps(threads, ppt, xyz, B, N, m, bs_log2, Q, cs, idx, new_xyz, st, false, nullptr);
 }
