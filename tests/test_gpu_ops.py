@@ -240,3 +240,36 @@ def test_fps_fused_new_xyz_output():
         idx, new_xyz = pointnet2_utils.fps_with_xyz(x, m)
         assert torch.equal(idx, _ext.furthest_point_sampling(x, m))
         assert torch.equal(new_xyz, torch.gather(x, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)))
+
+
+def test_empty_and_degenerate_inputs():
+    """zero-sized batches / queries / samples return empty tensors without launching; 1-point clouds work."""
+    z3 = torch.zeros((0, 16, 3), device=DEV)
+    assert _ext.furthest_point_sampling(z3, 4).shape == (0, 4)
+    x = cu(uniform_cloud(2, 64, seed=1))
+    assert _ext.furthest_point_sampling(x, 0).shape == (2, 0)
+    assert _ext.ball_query(x[:, :0].contiguous(), x, 0.2, 8).shape == (2, 0, 8)
+    assert _ext.ball_query(x[:, :5].contiguous(), x, 0.2, 0).shape == (2, 5, 0)
+    f = torch.randn(2, 3, 64, device=DEV)
+    assert _ext.group_points(f, torch.zeros((2, 0, 4), dtype=torch.int32, device=DEV)).shape == (2, 3, 0, 4)
+    g = _ext.group_points_grad(torch.zeros((2, 3, 0, 4), device=DEV), torch.zeros((2, 0, 4), dtype=torch.int32, device=DEV), 64)
+    assert g.shape == (2, 3, 64) and float(g.abs().sum()) == 0.0
+    d2, ix = _ext.three_nn(x[:, :0].contiguous(), x)
+    assert d2.shape == (2, 0, 3) and ix.shape == (2, 0, 3)
+    one = cu(uniform_cloud(1, 1, seed=2))
+    assert _ext.furthest_point_sampling(one, 3).cpu().tolist() == [[0, 0, 0]]
+    assert _ext.ball_query(one, one, 0.1, 4).cpu().tolist() == [[[0, 0, 0, 0]]]
+    # negative / zero radius: no hits -> zero rows (reference: d2 < r*r never true for r = 0)
+    assert int(_ext.ball_query(x[:, :7].contiguous(), x, 0.0, 4).abs().sum()) == 0
+
+
+def test_error_paths_raise():
+    x = cu(uniform_cloud(1, 32, seed=1))
+    with pytest.raises(RuntimeError, match="contiguous"):
+        _ext.furthest_point_sampling(x.transpose(1, 2).transpose(1, 2)[:, ::2], 4)
+    with pytest.raises(RuntimeError, match="float tensor"):
+        _ext.furthest_point_sampling(x.double(), 4)
+    with pytest.raises(RuntimeError, match="int tensor"):
+        _ext.gather_points(torch.randn(1, 3, 32, device=DEV), torch.zeros((1, 4), dtype=torch.int64, device=DEV))
+    with pytest.raises(RuntimeError, match="query_and_group"):
+        pointnet2_utils.fused_query_and_group(x, x[:, :4].contiguous(), None, 0.2, 256, True, True)  # nsample > 128
