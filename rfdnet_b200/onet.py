@@ -203,7 +203,10 @@ class DecoderCBatchNorm(nn.Module):
                 and self.hidden_size == 256 and self.n_blocks == 5)
         if fast:
             return self.decode(p, z, c)
-        # reference sequence, occ_decoder.py:110-122
+        return self.forward_reference(p, z, c)
+
+    def forward_reference(self, p, z, c):
+        """The reference's own op sequence in PyTorch (occ_decoder.py:110-122): training path and GPU yardstick."""
         p = p.transpose(1, 2)
         net = self.fc_p(p)
         if self.z_dim != 0:
