@@ -161,6 +161,8 @@ int rfd_onet_decode_f32(const float *p, long long p_batch_stride, int B, int T, 
                         float fc_out_b, float *logits, float *workspace, size_t workspace_bytes, void *stream);
 /* tcgen05 plumbing self-test: D (128,256) f32 = bf16(A (128,64)) . bf16(B (256,64))^T */
 int rfd_umma_selftest(const float *A, const float *B, float *D, void *stream);
+/* same product with the A operand staged in tensor memory (tcgen05.st.16x128b + TS-mode tcgen05.mma) */
+int rfd_umma_selftest_ts(const float *A, const float *B, float *D, void *stream);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,7 @@ SIGNATURES = {
     "rfd_onet_decode": [_vp, _ll, _i, _i, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp],
     "rfd_onet_decode_f32": [_vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _sz, _vp],
     "rfd_umma_selftest": [_vp, _vp, _vp, _vp],
+    "rfd_umma_selftest_ts": [_vp, _vp, _vp, _vp],
 }
 _RESTYPES = {"rfd_status_string": ctypes.c_char_p, "rfd_last_error": ctypes.c_char_p,
              "rfd_launch_count": _ll, "rfd_onet_packed_bytes": _sz, "rfd_onet_aff_floats": _sz, "rfd_sa_mlp_tc_packed_bytes": _sz}

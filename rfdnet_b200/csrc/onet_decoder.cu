@@ -23,6 +23,11 @@
 //   * weights (10 x 256 x 256 bf16, pre-swizzled by rfd_onet_pack_weights) stream from L2 through a 4-stage ring
 //     of 32-KB bulk copies (cp.async.bulk, mbarrier complete_tx) issued by a dedicated producer warp; each CTA owns a
 //     contiguous chunk of tiles, so the per-object affine table is reloaded only when the object changes;
+//   * tried, correct, but no faster (profiles/r1_decoder_history.md): TS-mode fc_1 -- the epilogue writes
+//     relu(cbn_1(net)) as packed bf16 back INTO tensor memory over net's own columns (tcgen05.st.16x128b) and the MMA
+//     reads A from TMEM, removing half of the A-panel shared-memory stores, the proxy fences and the A-operand
+//     shared-memory reads.  8.96 ms vs 8.67 ms: the layer time is a latency chain, not shared-memory bandwidth
+//     (the primitives and their self-test stay: umma::mma_bf16_ts, rfd_umma_selftest_ts);
 //   * tried and rejected (profiles/r1_decoder_history.md): issuing each layer as two N=128 halves so that the
 //     epilogue of the first half hides behind the MMAs of the second -- the A panels would have to be double
 //     buffered (WAR hazard on the in-place activation panels) and the N=128 MMAs re-read A twice, which made the
@@ -485,9 +490,84 @@ umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ Bm, 
   if (warp == 0) { umma::tc_fence_after(); umma::tmem_dealloc(tb, 256); }
 }
 
+// TS-mode self-test: same product, but A is first written into tensor memory (packed bf16 pairs) with
+// tcgen05.st.16x128b by threads that own (row, column-pair) positions in the 16x256b accumulator layout -- exactly what
+// the decoder's epilogue does -- and the MMA reads A from TMEM.
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_ts_kernel(const float *__restrict__ A, const float *__restrict__ Bm, float *__restrict__ D) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *sb = smem;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_barrier_init(); }
+  if (warp == 0) umma::tmem_alloc(&tmem_ptr, 512);
+  for (int e = tid; e < 256 * 32; e += 128) {
+    const int row = e / 32, k2 = (e % 32) * 2;
+    *reinterpret_cast<uint32_t *>(sb + umma::sw128_offset(row, k2)) = umma::pack_bf16x2(Bm[row * 64 + k2], Bm[row * 64 + k2 + 1]);
+  }
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tb = tmem_ptr;
+  const uint32_t ta = tb + 256;  // A lives in columns [256, 288): 64 k = 32 packed columns
+  // warp w owns lanes [32w, 32w+32); K = 64 -> four 16-column groups g (8 packed columns each)
+  for (int g = 0; g < 4; ++g) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t pk[2][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int row = warp * 32 + half * 16 + lr + 8 * jj;
+          const int k = g * 16 + 8 * i + 2 * lc;
+          pk[i][jj] = umma::pack_bf16x2(A[row * 64 + k], A[row * 64 + k + 1]);
+        }
+      umma::tmem_st_16x128b_x2(ta + ((uint32_t)(warp * 32 + half * 16) << 16) + g * 8, pk[0][0], pk[0][1], pk[1][0], pk[1][1]);
+    }
+  }
+  umma::tc_wait_st();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  if (tid == 0) {
+    constexpr uint32_t idesc = umma::make_idesc_bf16_f32(128, 256);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma::mma_bf16_ts(tb, ta + k * 8, umma::make_desc_k_sw128(umma::smem_u32(sb) + k * 32), idesc, k != 0);
+    umma::mma_commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::tc_fence_after();
+  for (int c0 = 0; c0 < 256; c0 += 32) {
+    uint32_t v[32];
+    umma::tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + c0, v);
+    umma::tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) D[(warp * 32 + lane) * 256 + c0 + j] = __uint_as_float(v[j]);
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { umma::tc_fence_after(); umma::tmem_dealloc(tb, 512); }
+}
+
 }  // namespace rfd
 
 using namespace rfd;
+
+extern "C" int rfd_umma_selftest_ts(const float *A, const float *Bm, float *D, void *stream) {
+  if (!A || !Bm || !D) return RFD_ERR_INVALID_ARGUMENT;
+  const int smem = DEC_H * 128 + 1024;
+  RFD_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                 "selftest_ts attr");
+  umma_selftest_ts_kernel<<<1, 128, smem, as_stream(stream)>>>(A, Bm, D);
+  RFD_CHECK_LAUNCH("umma_selftest_ts_kernel");
+  return RFD_OK;
+}
 
 extern "C" size_t rfd_onet_packed_bytes(int nsplit) {
   return nsplit == 1 ? (size_t)DEC_LAYERS * DEC_KP * DEC_STAGE_B : 0;

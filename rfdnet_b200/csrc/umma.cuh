@@ -171,6 +171,27 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] . B[smem]^T : the A operand (M=128 rows = lanes, K packed two bf16 per 32-bit column, 8 columns
+// per K=16 step) is read from tensor memory instead of shared memory.
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 lanes x 128 bit, 2 repeats (8 columns): thread l stores v[0] -> (lane base + l/4, col l%4), v[1] -> (+8 lanes, same
+// col), v[2] -> (lane base + l/4, col 4 + l%4), v[3] -> (+8 lanes)   (CuTe SM100_TMEM_STORE_16dp128b2x)
+__device__ __forceinline__ void tmem_st_16x128b_x2(uint32_t taddr, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x2.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v0), "r"(v1), "r"(v2),
+               "r"(v3)
+               : "memory");
+}
+
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void mma_commit(void *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -28,6 +28,20 @@ def test_umma_selftest():
     assert torch.allclose(D, ref, atol=1e-3, rtol=1e-4), float((D - ref).abs().max())
 
 
+def test_umma_selftest_ts():
+    """A operand from tensor memory (the layout the decoder's epilogue writes with tcgen05.st.16x128b)."""
+    lib = _lib.load()
+    torch.manual_seed(1)
+    A = torch.randn(128, 64, device=DEV)
+    B = torch.randn(256, 64, device=DEV)
+    D = torch.empty(128, 256, device=DEV)
+    _lib.check(lib.rfd_umma_selftest_ts(A.data_ptr(), B.data_ptr(), D.data_ptr(), torch.cuda.current_stream().cuda_stream),
+               "umma_selftest_ts")
+    torch.cuda.synchronize()
+    ref = A.bfloat16().float() @ B.bfloat16().float().t()
+    assert torch.allclose(D, ref, atol=1e-3, rtol=1e-4), float((D - ref).abs().max())
+
+
 def _decoder(seed=31):
     dec = onet.DecoderCBatchNorm(dim=3, z_dim=32, c_dim=512).eval()
     seeded_fill(dec, seed)
