@@ -159,6 +159,9 @@ int rfd_onet_decode(const float *p, long long p_batch_stride, int B, int T, cons
 int rfd_onet_decode_f32(const float *p, long long p_batch_stride, int B, int T, const float *fc_p_w,
                         const float *fc_w /*(10,256,256)*/, const float *aff, const float *fc_out_w,
                         float fc_out_b, float *logits, float *workspace, size_t workspace_bytes, void *stream);
+/* diagnostics: while `trace` (device, 2*10*16 unsigned long long) is non-NULL, rfd_onet_decode runs an instrumented
+ * kernel whose CTA 0 records clock64() at the MMA/epilogue hand-off points of its first two tiles. */
+int rfd_onet_decode_set_trace(unsigned long long *trace);
 /* tcgen05 plumbing self-test: D (128,256) f32 = bf16(A (128,64)) . bf16(B (256,64))^T */
 int rfd_umma_selftest(const float *A, const float *B, float *D, void *stream);
 /* same product with the A operand staged in tensor memory (tcgen05.st.16x128b + TS-mode tcgen05.mma) */

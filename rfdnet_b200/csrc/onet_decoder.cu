@@ -78,11 +78,15 @@ struct DecBars {
   uint32_t tmem_base;
 };
 
+// TRACE: CTA 0 records clock64() at the hand-off points of its first two tiles (diagnostics, rfd_onet_decode_trace):
+//   trace[tile][layer][0..3] MMA thread: operands of panel kp ready ; [4..7] MMAs of panel kp issued + committed
+//   trace[tile][layer][8]    epilogue warp 2: acc_ready observed     ; [9..12] panel kp published (a_ready arrive)
+template <bool TRACE>
 __global__ void __launch_bounds__(DEC_THREADS, 1)
 onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const float *__restrict__ fc_p_w,
                    const uint8_t *__restrict__ packed, const float *__restrict__ aff_all,
                    const float *__restrict__ fc_out_w, float fc_out_b, float *__restrict__ logits, int num_tiles,
-                   int tiles_per_obj) {
+                   int tiles_per_obj, unsigned long long *__restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *s_ah = smem + SM_AH;
@@ -132,7 +136,12 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // "A panel kp is complete" is signalled through HARDWARE named barriers 2+kp (bar.arrive by the 512 epilogue
+    // threads, bar.sync by this warp): the hand-off timeline (tools/trace_decoder.py) showed 250-500 cycles between
+    // the last epilogue warp publishing a panel through an mbarrier and this thread resuming from try_wait; the
+    // named barrier releases the waiting warp within tens of cycles.  MMA completion still uses tcgen05.commit ->
+    // mbarrier (the only completion mechanism of the async tensor pipe).
+    {
       constexpr uint32_t idesc = umma::make_idesc_bf16_f32(DEC_TILE_M, DEC_H);
       const uint32_t ah_addr = umma::smem_u32(s_ah), w_addr = umma::smem_u32(s_w);
       uint32_t st = 0, ph = 0, layer_count = 0;
@@ -140,17 +149,22 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
         for (int l = 0; l < DEC_LAYERS; ++l, ++layer_count) {
           const uint32_t d = (l & 1) ? tmem_x : tmem_n;  // fc_0 -> net (fresh), fc_1 -> accumulate onto x
           for (int kp = 0; kp < DEC_KP; ++kp) {
-            umma::mbar_wait(&bars->a_ready[kp], layer_count & 1u);
-            umma::mbar_wait(&bars->w_full[st], ph);
-            umma::tc_fence_after();
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + kp), "n"(32 * DEC_EPI_WARPS + 32) : "memory");
+            if (lane == 0) {
+              umma::mbar_wait(&bars->w_full[st], ph);
+              umma::tc_fence_after();
+              if (TRACE && blockIdx.x == 0 && tile - tile_lo < 2) trace[((tile - tile_lo) * DEC_LAYERS + l) * 16 + kp] = clock64();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = umma::make_desc_k_sw128(ah_addr + kp * DEC_PANEL_A + k * 32);
-              const uint64_t bd = umma::make_desc_k_sw128(w_addr + st * DEC_STAGE_B + k * 32);
-              umma::mma_bf16_ss(d, ad, bd, idesc, (l & 1) ? 1u : (uint32_t)((kp | k) != 0));
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = umma::make_desc_k_sw128(ah_addr + kp * DEC_PANEL_A + k * 32);
+                const uint64_t bd = umma::make_desc_k_sw128(w_addr + st * DEC_STAGE_B + k * 32);
+                umma::mma_bf16_ss(d, ad, bd, idesc, (l & 1) ? 1u : (uint32_t)((kp | k) != 0));
+              }
+              umma::mma_commit(&bars->w_empty[st]);  // frees the weight slot when these MMAs retire
+              if (kp == DEC_KP - 1) umma::mma_commit(&bars->acc_ready);
+              if (TRACE && blockIdx.x == 0 && tile - tile_lo < 2) trace[((tile - tile_lo) * DEC_LAYERS + l) * 16 + 4 + kp] = clock64();
             }
-            umma::mma_commit(&bars->w_empty[st]);  // frees the weight slot when these MMAs retire
-            if (kp == DEC_KP - 1) umma::mma_commit(&bars->acc_ready);
+            __syncwarp();
             if (++st == DEC_NSTAGE) { st = 0; ph ^= 1u; }
           }
         }
@@ -229,15 +243,19 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
           umma::tc_wait_st();
           umma::fence_proxy_async_smem();
           umma::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) umma::mbar_arrive(&bars->a_ready[kp]);
+          asm volatile("bar.arrive %0, %1;" ::"r"(2 + kp), "n"(32 * DEC_EPI_WARPS + 32) : "memory");
         }
       }
       // ---- layers
 #pragma unroll 1
       for (int l = 0; l < DEC_LAYERS; ++l, ++layer_count) {
+        // (a,c) of this warp's first panel are fetched while the MMAs of the layer are still running
+        const float4 pre0 = umma::lds_f4(affi_a + (l + 1) * (DEC_H * 2 * 4) + cq * (DEC_CW / 2) * 16);
+        const float4 pre1 = umma::lds_f4(affi_a + (l + 1) * (DEC_H * 2 * 4) + cq * (DEC_CW / 2) * 16 + 64);
         umma::mbar_wait(&bars->acc_ready, layer_count & 1u);
         umma::tc_fence_after();
+        const bool tr = TRACE && blockIdx.x == 0 && tile - tile_lo < 2 && warp == 2 && lane == 0;
+        if (tr) trace[((tile - tile_lo) * DEC_LAYERS + l) * 16 + 8] = clock64();
         const uint32_t src = ((l & 1) ? tmem_x : tmem_n) + lane_base + cq * DEC_CW;
         const uint32_t al = affi_a + (l + 1) * (DEC_H * 2 * 4) + cq * (DEC_CW / 2) * 16;  // + kp*512 + i*64
         // software pipeline over the four panels: the TMEM load of panel kp+1 is in flight while panel kp is
@@ -248,8 +266,9 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
         if (l < DEC_LAYERS - 1) {
 #pragma unroll
           for (int kp = 0; kp < DEC_KP; ++kp) {
-            const float4 ac0 = umma::lds_f4(al + kp * 512), ac1 = umma::lds_f4(al + kp * 512 + 64);
+            const float4 ac0 = kp ? umma::lds_f4(al + kp * 512) : pre0, ac1 = kp ? umma::lds_f4(al + kp * 512 + 64) : pre1;
             umma::tc_wait_ld();
+            if (tr && kp == 0) trace[((tile - tile_lo) * DEC_LAYERS + l) * 16 + 13] = clock64();
             if (kp + 1 < DEC_KP) {
               umma::tmem_ld_16x256b_x2(src + (kp + 1) * 64, v[(kp + 1) & 1][0]);
               umma::tmem_ld_16x256b_x2(src + (16u << 16) + (kp + 1) * 64, v[(kp + 1) & 1][1]);
@@ -266,10 +285,12 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
                 umma::sts_u32(pan + j * 1024 + sw, umma::pack_relu_bf16x2(fmaf(x0, ac.x, ac.z), fmaf(x1, ac.y, ac.w)));
               }
             }
+            if (tr && kp == 0) trace[((tile - tile_lo) * DEC_LAYERS + l) * 16 + 14] = clock64();
             umma::fence_proxy_async_smem();
+            if (tr && kp == 0) trace[((tile - tile_lo) * DEC_LAYERS + l) * 16 + 15] = clock64();
             umma::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) umma::mbar_arrive(&bars->a_ready[kp]);
+            asm volatile("bar.arrive %0, %1;" ::"r"(2 + kp), "n"(32 * DEC_EPI_WARPS + 32) : "memory");
+            if (tr) trace[((tile - tile_lo) * DEC_LAYERS + l) * 16 + 9 + kp] = clock64();
           }
         } else {
           // final: logits = fc_out(relu(cbn(x)))  -- fp32 dot product over the 256 channels
@@ -604,6 +625,8 @@ extern "C" int rfd_onet_cbn_tables(const float *c, int B, int c_dim, const float
   return RFD_OK;
 }
 
+static unsigned long long *g_decode_trace = nullptr;
+
 extern "C" int rfd_onet_decode(const float *p, long long p_batch_stride, int B, int T, const float *fc_p_w,
                                const void *packed, int nsplit, const float *aff, const float *fc_out_w,
                                float fc_out_b, float *logits, void *stream) {
@@ -617,13 +640,27 @@ extern "C" int rfd_onet_decode(const float *p, long long p_batch_stride, int B, 
   int dev = 0, sms = 148;
   RFD_CHECK_CUDA(cudaGetDevice(&dev), "decode getdevice");
   RFD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "decode sms");
-  RFD_CHECK_CUDA(cudaFuncSetAttribute(onet_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES),
-                 "decode attr");
   const int grid = (int)(num_tiles < sms ? num_tiles : sms);
-  onet_decode_kernel<<<grid, DEC_THREADS, DEC_SMEM_BYTES, as_stream(stream)>>>(
-      p, p_batch_stride, T, fc_p_w, reinterpret_cast<const uint8_t *>(packed), aff, fc_out_w, fc_out_b, logits,
-      (int)num_tiles, (int)tiles_per_obj);
+  if (g_decode_trace) {
+    RFD_CHECK_CUDA(cudaFuncSetAttribute(onet_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES),
+                   "decode attr");
+    onet_decode_kernel<true><<<grid, DEC_THREADS, DEC_SMEM_BYTES, as_stream(stream)>>>(
+        p, p_batch_stride, T, fc_p_w, reinterpret_cast<const uint8_t *>(packed), aff, fc_out_w, fc_out_b, logits,
+        (int)num_tiles, (int)tiles_per_obj, g_decode_trace);
+  } else {
+    RFD_CHECK_CUDA(cudaFuncSetAttribute(onet_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES),
+                   "decode attr");
+    onet_decode_kernel<false><<<grid, DEC_THREADS, DEC_SMEM_BYTES, as_stream(stream)>>>(
+        p, p_batch_stride, T, fc_p_w, reinterpret_cast<const uint8_t *>(packed), aff, fc_out_w, fc_out_b, logits,
+        (int)num_tiles, (int)tiles_per_obj, nullptr);
+  }
   RFD_CHECK_LAUNCH("onet_decode_kernel");
+  return RFD_OK;
+}
+
+// diagnostics: the next rfd_onet_decode calls record the hand-off timeline of CTA 0 into trace (2*10*16 u64); NULL = off
+extern "C" int rfd_onet_decode_set_trace(unsigned long long *trace) {
+  g_decode_trace = trace;
   return RFD_OK;
 }
 
