@@ -24,6 +24,7 @@
 //   * "no candidate" (all points skipped) reproduces the reference result old = 0.
 #include "common.cuh"
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 namespace rfd {
@@ -362,6 +363,7 @@ extern "C" int rfd_furthest_point_sampling_xyz(const float *xyz, int B, int N, i
         slot = maxc + 1;
       }
       const int maxc = slot - 1;
+      if (getenv("RFD_FPS_DEBUG")) fprintf(stderr, "[rfd fps] candidate cluster=%d ppt=%d max active clusters=%d\n", c, p, maxc);
       if (maxc <= 0) continue;  // e.g. a 16-CTA (non-portable) cluster is not schedulable on this part
       const int waves = (B + maxc - 1) / maxc;
       const double cost = waves * (0.55 + 0.034 * p);
@@ -375,5 +377,7 @@ extern "C" int rfd_furthest_point_sampling_xyz(const float *xyz, int B, int N, i
     cs = best_cs;
     ppt = best_ppt;
   }
+  if (getenv("RFD_FPS_DEBUG"))
+    fprintf(stderr, "[rfd fps] B=%d N=%d m=%d threads=%d cluster=%d points/thread=%d\n", B, N, m, threads, cs, ppt);
   return dispatch_fps(threads, ppt, xyz, B, N, m, bs_log2, Q, cs, idx, new_xyz, st, false, nullptr);
 }

@@ -16,9 +16,10 @@ from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
 
 
 class Pointnet2Backbone(nn.Module):
-    def __init__(self, input_feature_dim=1):
+    def __init__(self, input_feature_dim=1, fps_side_stream=False):
         super().__init__()
         self.input_feature_dim = input_feature_dim
+        self.fps_side_stream = fps_side_stream
         self.sa1 = PointnetSAModuleVotes(npoint=2048, radius=0.2, nsample=64,
                                          mlp=[self.input_feature_dim, 64, 64, 128], use_xyz=True, normalize_xyz=True)
         self.sa2 = PointnetSAModuleVotes(npoint=1024, radius=0.4, nsample=32, mlp=[128, 128, 128, 256],
@@ -32,23 +33,30 @@ class Pointnet2Backbone(nn.Module):
 
     def _forward_fused(self, xyz, features, end_points):
         """Inference schedule.  The four FPS runs only depend on coordinates (SA(k+1) samples the points SA(k)
-        sampled), so the serial FPS chain of SA2-4 runs on a side stream while the main stream does SA1's ball
-        query, grouping and shared MLP -- same kernels, same results, shorter critical path."""
-        main = torch.cuda.current_stream(xyz.device)
-        if getattr(self, "_side", None) is None or self._side.device != xyz.device:
-            self._side = torch.cuda.Stream(xyz.device)
-        side = self._side
+        sampled), so the serial FPS chain of SA2-4 CAN run on a side stream under SA1's ball query, grouping and
+        shared MLP (`fps_side_stream=True`).  Measured on B200 this is no faster (the one-CTA-per-scene FPS kernels
+        then share SMs with the MLP grid and slow down), so the default is the plain sequence."""
         i1, x1 = pointnet2_utils.fps_with_xyz(xyz.contiguous(), self.sa1.npoint)
-        side.wait_stream(main)
-        x1.record_stream(side)
-        with torch.cuda.stream(side):
+        if self.fps_side_stream:
+            main = torch.cuda.current_stream(xyz.device)
+            if getattr(self, "_side", None) is None or self._side.device != xyz.device:
+                self._side = torch.cuda.Stream(xyz.device)
+            side = self._side
+            side.wait_stream(main)
+            x1.record_stream(side)
+            with torch.cuda.stream(side):
+                i2, x2 = pointnet2_utils.fps_with_xyz(x1, self.sa2.npoint)
+                i3, x3 = pointnet2_utils.fps_with_xyz(x2, self.sa3.npoint)
+                i4, x4 = pointnet2_utils.fps_with_xyz(x3, self.sa4.npoint)
+            _, f1, _ = self.sa1(xyz, features, i1, x1)
+            main.wait_stream(side)
+            for t in (i2, x2, i3, x3, i4, x4):
+                t.record_stream(main)
+        else:
+            _, f1, _ = self.sa1(xyz, features, i1, x1)
             i2, x2 = pointnet2_utils.fps_with_xyz(x1, self.sa2.npoint)
             i3, x3 = pointnet2_utils.fps_with_xyz(x2, self.sa3.npoint)
             i4, x4 = pointnet2_utils.fps_with_xyz(x3, self.sa4.npoint)
-        _, f1, _ = self.sa1(xyz, features, i1, x1)
-        main.wait_stream(side)
-        for t in (i2, x2, i3, x3, i4, x4):
-            t.record_stream(main)
         _, f2, _ = self.sa2(x1, f1, i2, x2)
         _, f3, _ = self.sa3(x2, f2, i3, x3)
         _, f4, _ = self.sa4(x3, f3, i4, x4)
