@@ -182,6 +182,20 @@ def main():
     out.update(dec_c=c.numpy(), dec_sel=sel.numpy().astype(np.int32), dec_logits=logits.numpy(),
                dec_z2=z2.numpy(), dec_logits_z=logits_z.numpy())
 
+    # ---- G6 (section 8f rank 1): STN_Group, the per-proposal grouping of SkipPropagation (r = 1.0, nsample = 1024)
+    stn = M["p2m"].STN_Group(radius=1.0, nsample=1024, use_xyz=False, normalize_xyz=False).eval()
+    seeded_fill(stn, 41, scale=0.3)
+    pcs = torch.from_numpy(scannet_like_batch(1, 12000, seed0=55))
+    sxyz = pcs[..., :3].contiguous()
+    sfeat = torch.cat([pcs[..., 3:].transpose(1, 2), torch.randint(0, 5, (1, 1, 12000), generator=g).float()], dim=1).contiguous()
+    box_xyz = sxyz[:, torch.tensor([5, 900, 4000, 7777, 11000])].contiguous() + 0.05
+    orient = torch.tensor([[0.0, 0.7, -1.2, 2.5, 3.0]])
+    with torch.no_grad():
+        gx, gf = stn(sxyz, sfeat, box_xyz, orient)
+    out.update(stn_grouped_xyz=gx.numpy()[:, :, :, ::8], stn_grouped_feat_sum=gf.sum(-1).numpy(),
+               stn_feat_first=gf.numpy()[:, :, :, :4])
+    out["keys_stn_group"] = np.array([f"{k}:{tuple(v.shape)}" for k, v in stn.state_dict().items()])
+
     # ---- state_dict key/shape inventories of the reference modules (checkpoint compatibility of the mirrors)
     for name, mod in (("backbone", bb), ("voting", vm), ("detection", pm), ("decoder", dec)):
         sdm = mod.state_dict()

@@ -137,3 +137,27 @@ def test_detection_bf16_sa_path_close_to_fp32():
     assert torch.equal(ep["sa1_inds"], ep_b["sa1_inds"])
     f, fb = ep["sa1_features"], ep_b["sa1_features"]
     assert float((f - fb).abs().max()) <= 3e-2 * max(1.0, float(f.abs().max()))
+
+
+def test_stn_group_vs_reference_golden(golden):
+    """STN_Group (ball query r = 1.0, nsample = 1024 over the cloud, rotation, STN3d) on the
+    sm_100a kernels against the fixture produced by the reference's own STN_Group on CPU."""
+    from rfdnet_b200 import stn_group
+    stn = stn_group.STN_Group(radius=1.0, nsample=1024, use_xyz=False, normalize_xyz=False).eval()
+    seeded_fill(stn, 41, scale=0.3)
+    stn = stn.to(DEV)
+    g = torch.Generator().manual_seed(3)
+    # keep the generator in step with tests/golden/make_golden.py (G2, G3, G5 draws precede G6)
+    torch.randn(2, 5, 1024, generator=g); torch.randn(2, 16, 300, generator=g); torch.randn(2, 64, 64, generator=g)
+    torch.randn(3, 512, generator=g); torch.randn(3, 32, generator=g)
+    pcs = torch.from_numpy(scannet_like_batch(1, 12000, seed0=55))
+    sxyz = pcs[..., :3].contiguous()
+    sfeat = torch.cat([pcs[..., 3:].transpose(1, 2), torch.randint(0, 5, (1, 1, 12000), generator=g).float()], dim=1).contiguous()
+    box_xyz = sxyz[:, torch.tensor([5, 900, 4000, 7777, 11000])].contiguous() + 0.05
+    orient = torch.tensor([[0.0, 0.7, -1.2, 2.5, 3.0]])
+    with torch.no_grad():
+        gx, gf = stn(sxyz.to(DEV), sfeat.to(DEV), box_xyz.to(DEV), orient.to(DEV))
+    assert gx.shape == (1, 3, 5, 1024) and gf.shape == (1, 2, 5, 1024)
+    assert np.array_equal(gf.cpu().numpy()[:, :, :, :4], golden["stn_feat_first"])           # gathered rows: exact
+    assert np.allclose(gf.sum(-1).cpu().numpy(), golden["stn_grouped_feat_sum"], rtol=1e-5, atol=1e-3)
+    assert np.allclose(gx.cpu().numpy()[:, :, :, ::8], golden["stn_grouped_xyz"], atol=2e-4, rtol=1e-4)

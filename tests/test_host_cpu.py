@@ -56,8 +56,10 @@ def test_ops_fail_loudly_without_gpu():
 
 
 def test_state_dict_keys_match_reference(golden):
+    from rfdnet_b200 import stn_group
     mods = {"backbone": detection.Pointnet2Backbone(1), "voting": detection.VotingModule(1, 256),
-            "detection": detection.ProposalModule(), "decoder": onet.DecoderCBatchNorm(z_dim=32, c_dim=512)}
+            "detection": detection.ProposalModule(), "decoder": onet.DecoderCBatchNorm(z_dim=32, c_dim=512),
+            "stn_group": stn_group.STN_Group(radius=1.0, nsample=1024, use_xyz=False)}
     for name, m in mods.items():
         mine = [f"{k}:{tuple(v.shape)}" for k, v in m.state_dict().items()]
         ref = [str(x) for x in golden[f"keys_{name}"]]
