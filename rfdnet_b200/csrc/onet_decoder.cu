@@ -676,13 +676,20 @@ extern "C" int rfd_onet_decode_f32(const float *p, long long p_batch_stride, int
   if (bc > B) bc = B;
   if (bc > 65535) bc = 65535;
   cudaStream_t st = as_stream(stream);
-  static float *ones_zeros = nullptr;  // unit scale / zero shift for the bias-free layers
-  if (!ones_zeros) {
+  // unit scale / zero shift for the bias-free layers: one small constant buffer per device, created on first use
+  static float *ones_zeros_dev[64] = {nullptr};
+  int cur_dev = 0;
+  RFD_CHECK_CUDA(cudaGetDevice(&cur_dev), "decode_f32 getdevice");
+  if (cur_dev < 0 || cur_dev >= 64) return RFD_ERR_UNSUPPORTED_SIZE;
+  if (!ones_zeros_dev[cur_dev]) {
     float h[2 * DEC_H];
     for (int i = 0; i < DEC_H; ++i) { h[i] = 1.f; h[DEC_H + i] = 0.f; }
-    RFD_CHECK_CUDA(cudaMalloc(&ones_zeros, sizeof(h)), "decode_f32 malloc");
-    RFD_CHECK_CUDA(cudaMemcpy(ones_zeros, h, sizeof(h), cudaMemcpyHostToDevice), "decode_f32 memcpy");
+    float *d = nullptr;
+    RFD_CHECK_CUDA(cudaMalloc(&d, sizeof(h)), "decode_f32 malloc");
+    RFD_CHECK_CUDA(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice), "decode_f32 memcpy");
+    ones_zeros_dev[cur_dev] = d;
   }
+  float *ones_zeros = ones_zeros_dev[cur_dev];
   for (int b0 = 0; b0 < B; b0 += (int)bc) {
     const int nb = (int)((B - b0) < bc ? (B - b0) : bc);
     float *x = workspace, *net = workspace + (size_t)bc * DEC_H * T;
