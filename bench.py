@@ -317,7 +317,21 @@ def main():
     if not os.path.exists(os.path.join(ROOT, "rfdnet_b200", "librfdnet_b200.so")):
         g.build()
     from rfdnet_b200 import dist as D
-    D.init_from_env("nccl")
+    # NCCL prints its version banner on STDOUT when the first communicator is created; keep stdout for the one JSON
+    # line: route fd 1 to stderr during initialisation + the first collective, then restore it.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        D.init_from_env("nccl")
+        if world > 1:
+            torch.cuda.set_device(local)
+            D.barrier()
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     run_gpu(args, rank, world, local)
     if world > 1:
         torch.distributed.destroy_process_group()
