@@ -192,3 +192,17 @@ def test_gloo_world2_gradient_allreduce(tmp_path):
                        capture_output=True, text=True, env=env, timeout=280)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("-ok") == 2 and "rank0" in r.stdout and "rank1" in r.stdout, r.stdout
+
+
+def test_c_abi_from_plain_c(lib, tmp_path):
+    """Compile a C99 program against include/rfdnet_b200.h with gcc, link it to librfdnet_b200.so and run it."""
+    from rfdnet_b200 import _lib
+    exe = tmp_path / "abi_check"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", "abi_check.c"), "-o", str(exe), "-L", libdir, "-lrfdnet_b200",
+           "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "abi_check ok" in r.stdout, r.stdout + r.stderr
