@@ -123,6 +123,12 @@ int rfd_sa_mlp_tc_pack(const float *W1, const float *scale1, const float *W2, co
                        const float *scale3, int Ct, int C1, int C2, int C3, void *packed, void *stream);
 int rfd_sa_mlp_tc(const float *x, int B, int Ct, int M, int S, const void *packed, const float *shift, int C1, int C2,
                   int C3, float *out, void *stream);
+/* full set-abstraction fusion: same kernel, but the (B,3+C,M,S) grouped tensor is never
+ * materialised -- the A tiles are gathered from xyz (B,N,3) / features (B,C,N) through idx (B,M,S) (rfd_ball_query),
+ * centred on new_xyz (B,M,3) and scaled by 1/radius when normalize_xyz, exactly as rfd_query_and_group would. */
+int rfd_sa_gather_mlp_tc(const float *xyz, const float *new_xyz, const float *features, const int *idx, int B, int N,
+                         int M, int S, int C, float radius, int normalize_xyz, const void *packed, const float *shift,
+                         int C1, int C2, int C3, float *out, void *stream);
 
 /* ---- (a13) occupancy query lattice: out (R^3,3) f32 = box_size * linspace(-0.5,0.5,R) on each axis, z fastest */
 int rfd_make_3d_grid(int R, float box_size, float *out, void *stream);

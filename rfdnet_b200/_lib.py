@@ -34,6 +34,7 @@ SIGNATURES = {
     "rfd_sa_mlp_tc_packed_bytes": [_i, _i, _i, _i],
     "rfd_sa_mlp_tc_pack": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "rfd_sa_mlp_tc": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "rfd_sa_gather_mlp_tc": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
     "rfd_onet_packed_bytes": [_i],
     "rfd_onet_pack_weights": [_vp, _i, _vp, _vp],
     "rfd_onet_aff_floats": [],

@@ -41,7 +41,15 @@ struct SaBars {
 };
 
 struct SaParams {
-  const float *x;        // (B, Ct, L) grouped tensor, L = M*S
+  // gather mode (idx != nullptr): the grouped tile is never materialised -- rows are gathered straight from the
+  // point cloud: channel c < 3: (xyz[idx][c] - new_xyz[m][c]) * inv_r ; c >= 3: features[c-3][idx]
+  const int *idx;        // (B, M, S) ball-query result, or nullptr
+  const float *xyz;      // (B, N, 3)
+  const float *new_xyz;  // (B, M, 3)
+  const float *feat;     // (B, Ct-3, N) or nullptr
+  int N;
+  float inv_r;           // 1/radius when normalize_xyz, else 1
+  const float *x;        // (B, Ct, L) grouped tensor, L = M*S  (materialised mode)
   const uint8_t *w;      // packed weights: stages (layer, k-panel), each n[layer]*128 bytes
   const float *shift;    // [C1 + C2 + C3]
   float *out;            // (B, C3, M)
@@ -133,15 +141,36 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_mlp_tc_kernel(const SaParams
       // ---- A0: grouped tile -> bf16 swizzled panels.  thread = (row r, 8-channel chunk c8); a warp covers 32
       // consecutive rows of one chunk: coalesced 128-B global reads, conflict-free 16-B shared stores.
       {
-        const float *xb = P.x + (size_t)b * P.Ct * P.L;
         const int r = et & 127;
         const bool rv = (l0 + r) < P.L;
+        int pk = 0;
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        if (P.idx && rv) {
+          pk = __ldg(P.idx + (size_t)b * P.L + l0 + r);
+          const float *nc = P.new_xyz + ((size_t)b * P.M + (l0 + r) / P.S) * 3;
+          cx = __ldg(nc); cy = __ldg(nc + 1); cz = __ldg(nc + 2);
+        }
+        const float *xb = P.idx ? nullptr : P.x + (size_t)b * P.Ct * P.L;
+        const float *pb = P.idx ? P.xyz + ((size_t)b * P.N + pk) * 3 : nullptr;
+        const float *fb = (P.idx && P.feat) ? P.feat + (size_t)b * (P.Ct - 3) * P.N + pk : nullptr;
         for (int c8 = et >> 7; c8 < P.kp[0] * 8; c8 += 4) {
           float f[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int c = c8 * 8 + u;
-            f[u] = (rv && c < P.Ct) ? __ldg(xb + (size_t)c * P.L + l0 + r) : 0.f;
+            float v = 0.f;
+            if (rv && c < P.Ct) {
+              if (!P.idx) {
+                v = __ldg(xb + (size_t)c * P.L + l0 + r);
+              } else if (c < 3) {
+                // same arithmetic as query_and_group_kernel: (p - centre), then * (1/r)
+                v = __fsub_rn(__ldg(pb + c), c == 0 ? cx : (c == 1 ? cy : cz));
+                if (P.inv_r != 1.0f) v = __fmul_rn(v, P.inv_r);
+              } else {
+                v = __ldg(fb + (size_t)(c - 3) * P.N);
+              }
+            }
+            f[u] = v;
           }
           const uint32_t dst = a_base + (c8 >> 3) * SA_PANEL + r * 128 + ((((c8 & 7) ^ (r & 7))) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(umma::pack_bf16x2(f[0], f[1])),
@@ -309,15 +338,11 @@ extern "C" int rfd_sa_mlp_tc_pack(const float *W1, const float *scale1, const fl
   return RFD_OK;
 }
 
-extern "C" int rfd_sa_mlp_tc(const float *x, int B, int Ct, int M, int S, const void *packed, const float *shift,
-                             int C1, int C2, int C3, float *out, void *stream) {
-  if (B < 0 || M < 0 || S < 1) return RFD_ERR_INVALID_ARGUMENT;
-  if (B == 0 || M == 0) return RFD_OK;
-  if (!x || !packed || !shift || !out) return RFD_ERR_INVALID_ARGUMENT;
+static int sa_launch(SaParams &P, int B, int Ct, int M, int S, const void *packed, const float *shift, int C1, int C2,
+                     int C3, float *out, void *stream) {
   if (rfd_sa_mlp_tc_packed_bytes(Ct, C1, C2, C3) == 0) return RFD_ERR_UNSUPPORTED_SIZE;
   if (!(S == 16 || S == 32 || S == 64 || S == 128)) return RFD_ERR_UNSUPPORTED_SIZE;
-  SaParams P;
-  P.x = x; P.w = reinterpret_cast<const uint8_t *>(packed); P.shift = shift; P.out = out;
+  P.w = reinterpret_cast<const uint8_t *>(packed); P.shift = shift; P.out = out;
   P.B = B; P.Ct = Ct; P.M = M; P.S = S; P.L = M * S;
   P.kp[0] = sa_kp0(Ct); P.kp[1] = C1 / 64; P.kp[2] = C2 / 64;
   P.n[0] = C1; P.n[1] = C2; P.n[2] = C3;
@@ -336,4 +361,26 @@ extern "C" int rfd_sa_mlp_tc(const float *x, int B, int Ct, int M, int S, const 
   sa_mlp_tc_kernel<<<grid, SA_THREADS, SA_SMEM_BYTES, st>>>(P);
   RFD_CHECK_LAUNCH("sa_mlp_tc_kernel");
   return RFD_OK;
+}
+
+extern "C" int rfd_sa_mlp_tc(const float *x, int B, int Ct, int M, int S, const void *packed, const float *shift,
+                             int C1, int C2, int C3, float *out, void *stream) {
+  if (B < 0 || M < 0 || S < 1) return RFD_ERR_INVALID_ARGUMENT;
+  if (B == 0 || M == 0) return RFD_OK;
+  if (!x || !packed || !shift || !out) return RFD_ERR_INVALID_ARGUMENT;
+  SaParams P = {};
+  P.x = x;
+  return sa_launch(P, B, Ct, M, S, packed, shift, C1, C2, C3, out, stream);
+}
+
+extern "C" int rfd_sa_gather_mlp_tc(const float *xyz, const float *new_xyz, const float *features, const int *idx, int B,
+                                    int N, int M, int S, int C, float radius, int normalize_xyz, const void *packed,
+                                    const float *shift, int C1, int C2, int C3, float *out, void *stream) {
+  if (B < 0 || M < 0 || S < 1 || N < 1 || C < 0) return RFD_ERR_INVALID_ARGUMENT;
+  if (B == 0 || M == 0) return RFD_OK;
+  if (!xyz || !new_xyz || !idx || (C > 0 && !features) || !packed || !shift || !out) return RFD_ERR_INVALID_ARGUMENT;
+  SaParams P = {};
+  P.idx = idx; P.xyz = xyz; P.new_xyz = new_xyz; P.feat = C > 0 ? features : nullptr; P.N = N;
+  P.inv_r = normalize_xyz ? 1.0f / radius : 1.0f;
+  return sa_launch(P, B, 3 + C, M, S, packed, shift, C1, C2, C3, out, stream);
 }

@@ -97,3 +97,20 @@ class PackedMlp3:
                                                  self.shift.data_ptr(), self.C1, self.C2, self.C3, out.data_ptr(),
                                                  torch.cuda.current_stream().cuda_stream), "sa_mlp_tc")
         return out
+
+    def fused(self, xyz, new_xyz, features, idx, radius, normalize_xyz):
+        """Full SA fusion: gather + centre/normalise + 3-layer MLP + max without materialising the grouped tensor.
+        xyz (B,N,3), new_xyz (B,M,3), features (B,C,N) or None, idx (B,M,S) i32 -> (B, C3, M)."""
+        B, N, _ = xyz.shape
+        _, M, S = idx.shape
+        C = 0 if features is None else features.shape[1]
+        assert 3 + C == self.Ct
+        out = torch.empty((B, self.C3, M), dtype=torch.float32, device=xyz.device)
+        flop = 2.0 * B * M * S * (self.Ct * self.C1 + self.C1 * self.C2 + self.C2 * self.C3)
+        with torch.cuda.device(xyz.device), _lib.timed("sa_mlp_tc", flop):
+            _lib.check(_lib.load().rfd_sa_gather_mlp_tc(
+                xyz.data_ptr(), new_xyz.data_ptr(), 0 if features is None else features.data_ptr(), idx.data_ptr(),
+                B, N, M, S, C, float(radius), int(bool(normalize_xyz)), self.packed.data_ptr(), self.shift.data_ptr(),
+                self.C1, self.C2, self.C3, out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                "sa_gather_mlp_tc")
+        return out

@@ -61,6 +61,7 @@ class PointnetSAModuleVotes(_FoldCache, nn.Module):
                  precision: str = 'fp32'):
         super().__init__()
         self.precision = precision  # 'fp32' (exact CUDA-core path) | 'bf16' (tcgen05 shared-MLP, eval only)
+        self.fuse_gather = False    # bf16 only: gather inside the MLP kernel, the grouped tensor is never materialised
         self.npoint, self.radius, self.nsample = npoint, radius, nsample
         self.pooling = pooling
         self.use_xyz = use_xyz
@@ -104,11 +105,19 @@ class PointnetSAModuleVotes(_FoldCache, nn.Module):
         else:
             assert inds.shape[1] == self.npoint
             new_xyz = pointnet2_utils._ext.gather_points(xyz.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
+        layers = self._folded(self.mlp_module)
+        if (self.precision == 'bf16' and self.fuse_gather and self.use_xyz and len(layers) == 3
+                and self.nsample in (16, 32, 64)):
+            if getattr(self, "_tc", None) is None:
+                self._tc = _mlp.PackedMlp3(layers)
+            if self._tc.ok:
+                idx = pointnet2_utils._ext.ball_query(new_xyz, xyz, self.radius, self.nsample)
+                feats = None if features is None else features.contiguous()
+                return new_xyz, self._tc.fused(xyz, new_xyz, feats, idx, self.radius, self.normalize_xyz), inds
         grouped, _, _ = pointnet2_utils.fused_query_and_group(
             xyz, new_xyz, None if features is None else features.contiguous(), self.radius, self.nsample,
             self.use_xyz, self.normalize_xyz)
         Ct = grouped.shape[1]
-        layers = self._folded(self.mlp_module)
         if self.precision == 'bf16' and len(layers) == 3 and self.nsample in (16, 32, 64):
             if getattr(self, "_tc", None) is None:
                 self._tc = _mlp.PackedMlp3(layers)

@@ -161,3 +161,23 @@ def test_stn_group_vs_reference_golden(golden):
     assert np.array_equal(gf.cpu().numpy()[:, :, :, :4], golden["stn_feat_first"])           # gathered rows: exact
     assert np.allclose(gf.sum(-1).cpu().numpy(), golden["stn_grouped_feat_sum"], rtol=1e-5, atol=1e-3)
     assert np.allclose(gx.cpu().numpy()[:, :, :, ::8], golden["stn_grouped_xyz"], atol=2e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("N,npoint,radius,S,C,mlp", [(4096, 512, 0.3, 32, 5, [5, 64, 64, 128]), (2048, 1024, 0.4, 32, 128, [128, 128, 128, 256]),
+                                                     (1024, 256, 0.3, 16, 256, [256, 128, 128, 128]), (20000, 2048, 0.2, 64, 1, [1, 64, 64, 128])])
+def test_full_sa_fusion_equals_materialised_path(N, npoint, radius, S, C, mlp):
+    """gather + centre/normalise + 3-layer tcgen05 MLP + max WITHOUT materialising the grouped tensor
+    must be bit-identical to the same tensor-core kernel fed with the materialised (B,3+C,M,S) tensor."""
+    sa = pointnet2_modules.PointnetSAModuleVotes(npoint=npoint, radius=radius, nsample=S, mlp=list(mlp), use_xyz=True,
+                                                 normalize_xyz=True, precision='bf16').eval()
+    seeded_fill(sa, N + S)
+    sa = sa.to(DEV)
+    xyz = torch.from_numpy(scannet_like_batch(2, N, seed0=N)[..., :3].copy()).to(DEV)
+    g = torch.Generator().manual_seed(C)
+    feats = torch.randn(2, C, N, generator=g).to(DEV)
+    with torch.no_grad():
+        x1, f1, i1 = sa(xyz, feats)
+        sa.fuse_gather = True
+        x2, f2, i2 = sa(xyz, feats)
+    assert torch.equal(i1, i2) and torch.equal(x1, x2)
+    assert torch.equal(f1, f2)
