@@ -61,7 +61,7 @@ class PointnetSAModuleVotes(_FoldCache, nn.Module):
                  precision: str = 'fp32'):
         super().__init__()
         self.precision = precision  # 'fp32' (exact CUDA-core path) | 'bf16' (tcgen05 shared-MLP, eval only)
-        self.fuse_gather = False    # bf16 only: gather inside the MLP kernel, the grouped tensor is never materialised
+        self.fuse_gather = True     # bf16 only: gather inside the MLP kernel, the grouped tensor is never materialised
         self.npoint, self.radius, self.nsample = npoint, radius, nsample
         self.pooling = pooling
         self.use_xyz = use_xyz

@@ -176,6 +176,7 @@ def test_full_sa_fusion_equals_materialised_path(N, npoint, radius, S, C, mlp):
     g = torch.Generator().manual_seed(C)
     feats = torch.randn(2, C, N, generator=g).to(DEV)
     with torch.no_grad():
+        sa.fuse_gather = False
         x1, f1, i1 = sa(xyz, feats)
         sa.fuse_gather = True
         x2, f2, i2 = sa(xyz, feats)
