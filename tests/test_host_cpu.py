@@ -206,3 +206,26 @@ def test_c_abi_from_plain_c(lib, tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "abi_check ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_dropin_install_registers_ext():
+    """after dropin.install(), `import pointnet2_ops._ext` resolves to rfdnet_b200._ext and
+    exposes the reference's nine function names (bindings.cpp:6-19)."""
+    import importlib
+    saved = {k: sys.modules.get(k) for k in ("pointnet2_ops", "pointnet2_ops._ext")}
+    try:
+        sys.modules.pop("pointnet2_ops", None)
+        sys.modules.pop("pointnet2_ops._ext", None)
+        from rfdnet_b200 import dropin
+        ext = dropin.install()
+        mod = importlib.import_module("pointnet2_ops._ext")
+        assert mod is ext
+        for name in ("gather_points", "gather_points_grad", "furthest_point_sampling", "three_nn", "three_interpolate",
+                     "three_interpolate_grad", "ball_query", "group_points", "group_points_grad"):
+            assert callable(getattr(mod, name)), name
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
