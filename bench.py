@@ -274,7 +274,7 @@ def run_gpu(args, rank, world, local):
                    "parallelism": f"dp{world} (scenes sharded, no collective)",
                    "l2": "per-step working set (logits %d MB + clouds) exceeds the 126 MB L2; inputs rotate over 2 sets"
                          % (S * 256 * 32768 * 4 // 2 ** 20)},
-        "roofline": {"kernel": "onet_decode_kernel", "bound": "tensor", "achieved": dec_tflops, "peak": tc_sust / 1e0 if tc_sust < 1e4 else tc_sust,
+        "roofline": {"kernel": "onet_decode_kernel", "bound": "tensor", "achieved": dec_tflops, "peak": tc_sust,
                      "unit": "TFLOP/s", "frac": dec_tflops / tc_sust, "traffic": traffic,
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})", "ms_per_launch": dec_ms,
                      "flop_per_launch": float(np.mean([w for _, w in dec]))},

@@ -28,7 +28,9 @@ def build_shared_mlp(mlp_spec: List[int], bn: bool = True):
 
 
 class _FoldCache:
-    """Lazily folded (W, scale, shift, relu) per layer; dropped on train() / load_state_dict()."""
+    """Lazily folded (W, scale, shift, relu) per layer; dropped on train()/eval(), load_state_dict() and .to()/.cuda().
+    Parameters modified IN PLACE while the module stays in eval mode (e.g. an optimizer step without a mode switch)
+    are not noticed: call `module.eval()` again (or `_drop()`) after such an update."""
 
     def _folded(self, seq):
         if getattr(self, "_fold", None) is None:
