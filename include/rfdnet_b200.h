@@ -133,6 +133,11 @@ int rfd_sa_gather_mlp_tc(const float *xyz, const float *new_xyz, const float *fe
 /* ---- (a13) occupancy query lattice: out (R^3,3) f32 = box_size * linspace(-0.5,0.5,R) on each axis, z fastest */
 int rfd_make_3d_grid(int R, float box_size, float *out, void *stream);
 
+/* ---- occupancy mask (first step): logits (B,T) f32 -> bits (B, ceil(T/32)) u32 with bit t%32 of
+ * word t/32 set iff logit >= threshold (the reference thresholds at logit(0.5) = 0, generator.py:160;
+ * external/common.py:7-35 compute_iou), counts (B) i32 = occupied points per object (NULL = skip). */
+int rfd_occupancy_bits(const float *logits, int B, int T, float threshold, uint32_t *bits, int *counts, void *stream);
+
 /* ---- (a12) ONet decoder (DecoderCBatchNorm, eval mode), hidden = 256, n_blocks = 5.
  * Step 1 (once per checkpoint): pack the fp32 fc weights into the device layout the kernel streams:
  *   fc_w (10,256,256) f32 = [blocks.0.fc_0, blocks.0.fc_1, blocks.1.fc_0, ...].weight  ([out][in])

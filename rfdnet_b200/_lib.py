@@ -31,6 +31,7 @@ SIGNATURES = {
     "rfd_three_nn_interpolate": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "rfd_pointwise_mlp_f32": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "rfd_make_3d_grid": [_i, _f, _vp, _vp],
+    "rfd_occupancy_bits": [_vp, _i, _i, _f, _vp, _vp, _vp],
     "rfd_sa_mlp_tc_packed_bytes": [_i, _i, _i, _i],
     "rfd_sa_mlp_tc_pack": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "rfd_sa_mlp_tc": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],

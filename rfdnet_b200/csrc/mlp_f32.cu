@@ -125,9 +125,47 @@ __global__ void make_3d_grid_kernel(int R, float box, float *__restrict__ out) {
   out[(size_t)e * 3 + 2] = __fmul_rn(box, lin(iz));
 }
 
+// occupancy bit mask: bit (t % 32) of word (t / 32) of object b is set iff logits[b][t] >= threshold; counts[b] = number
+// of occupied points.  First step of the dense-grid -> surface hand-off: callers that only need
+// occupancy (voxel IoU, external/common.py:7-35; the `logit >= 0` decision of generator.py:160) copy 1 bit instead of
+// 32 per query point back to the host.
+__global__ void __launch_bounds__(256)
+occupancy_bits_kernel(const float *__restrict__ logits, int T, float threshold, uint32_t *__restrict__ bits,
+                      int *__restrict__ counts) {
+  const int b = blockIdx.y;
+  const int words = (T + 31) / 32;
+  const float *lg = logits + (size_t)b * T;
+  int local = 0;
+  for (int t0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; t0 < words * 32; t0 += gridDim.x * blockDim.x) {
+    const int t = t0 + (threadIdx.x & 31);
+    const bool occ = t < T && __ldg(lg + t) >= threshold;
+    const unsigned m = __ballot_sync(0xffffffffu, occ);
+    if ((threadIdx.x & 31) == 0) {
+      bits[(size_t)b * words + t0 / 32] = m;
+      local += __popc(m);
+    }
+  }
+  if (counts && (threadIdx.x & 31) == 0 && local) atomicAdd(counts + b, local);
+}
+
 }  // namespace rfd
 
 using namespace rfd;
+
+extern "C" int rfd_occupancy_bits(const float *logits, int B, int T, float threshold, uint32_t *bits, int *counts,
+                                  void *stream) {
+  if (B < 0 || T < 0) return RFD_ERR_INVALID_ARGUMENT;
+  if (B == 0 || T == 0) return RFD_OK;
+  if (!logits || !bits) return RFD_ERR_INVALID_ARGUMENT;
+  if (B > 65535) return RFD_ERR_UNSUPPORTED_SIZE;
+  cudaStream_t st = as_stream(stream);
+  if (counts) RFD_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)B, st), "occupancy_bits memset");
+  int gx = h_ceil_div(T, 256);
+  if (gx > 64) gx = 64;
+  occupancy_bits_kernel<<<dim3(gx, B), 256, 0, st>>>(logits, T, threshold, bits, counts);
+  RFD_CHECK_LAUNCH("occupancy_bits_kernel");
+  return RFD_OK;
+}
 
 int rfd::launch_pointwise_f32(const float *x, const float *W, const float *scale, const float *shift,
                               const float *residual, const float *pre_scale, const float *pre_shift,

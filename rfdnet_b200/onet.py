@@ -225,3 +225,17 @@ def make_3d_grid(resolution=32, box_size=1.1, device='cuda'):
         _lib.check(_lib.load().rfd_make_3d_grid(int(resolution), float(box_size), out.data_ptr(),
                                                 torch.cuda.current_stream().cuda_stream), "make_3d_grid")
     return out
+
+
+def occupancy_bits(logits, threshold=0.0):
+    """logits (B,T) f32 cuda -> (bits (B, ceil(T/32)) int32 [bit t%32 of word t/32 = logit >= threshold], counts (B) i32).
+    threshold 0.0 = logit(0.5), the reference's surface level (generator.py:160)."""
+    logits = logits.contiguous()
+    B, T = logits.shape
+    bits = torch.empty((B, (T + 31) // 32), dtype=torch.int32, device=logits.device)
+    counts = torch.empty((B,), dtype=torch.int32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        _lib.check(_lib.load().rfd_occupancy_bits(logits.data_ptr(), B, T, float(threshold), bits.data_ptr(),
+                                                  counts.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "occupancy_bits")
+    return bits, counts

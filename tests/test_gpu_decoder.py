@@ -118,3 +118,17 @@ def test_decoder_full_grid_properties():
         ref = dec.decode(sub, z, c, precision="fp32")
     scale = float(ref.abs().max())
     assert float((full[:, ::37] - ref).abs().max()) <= BF16_REL_TOL * max(1.0, scale)
+
+
+@pytest.mark.parametrize("B,T", [(3, 32768), (5, 1000), (1, 1), (2, 33)])
+def test_occupancy_bits_exact(B, T):
+    g = torch.Generator().manual_seed(B * 7 + T)
+    logits = torch.randn(B, T, generator=g).to(DEV)
+    logits[0, 0] = 0.0  # exactly on the threshold counts as occupied (>=)
+    bits, counts = onet.occupancy_bits(logits, 0.0)
+    occ = (logits >= 0.0).cpu().numpy()
+    assert np.array_equal(counts.cpu().numpy(), occ.sum(1).astype(np.int32))
+    pad = np.zeros((B, (T + 31) // 32 * 32), bool)
+    pad[:, :T] = occ
+    words = (pad.reshape(B, -1, 32) * (1 << np.arange(32, dtype=np.uint64))).sum(-1).astype(np.uint32)
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), words)
