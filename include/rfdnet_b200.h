@@ -49,7 +49,7 @@ extern "C" {
 #define RFD_ERR_CUDA (-3)             /* a CUDA runtime call or launch failed; see rfd_last_error() */
 #define RFD_ERR_NO_DEVICE (-4)        /* no sm_100 device / wrong architecture */
 
-#define RFD_ABI_VERSION 1
+#define RFD_ABI_VERSION 2
 
 int rfd_abi_version(void);
 const char *rfd_status_string(int status);
@@ -141,8 +141,8 @@ int rfd_occupancy_bits(const float *logits, int B, int T, float threshold, uint3
 /* ---- (a12) ONet decoder (DecoderCBatchNorm, eval mode), hidden = 256, n_blocks = 5.
  * Step 1 (once per checkpoint): pack the fp32 fc weights into the device layout the kernel streams:
  *   fc_w (10,256,256) f32 = [blocks.0.fc_0, blocks.0.fc_1, blocks.1.fc_0, ...].weight  ([out][in])
- *   -> packed (rfd_onet_packed_bytes(1) bytes): bf16, one 32-KB image per (layer, 64-wide K panel) of the
- *      UMMA K-major 128B-swizzled B operand, in consumption order.
+ *   -> packed (rfd_onet_packed_bytes(mode) bytes): 16-bit operands, one 32-KB image per (layer, 64-wide K panel) of
+ *      the UMMA K-major 128B-swizzled B operand, in consumption order (MODE_F16X3: hi image then lo image).
  * Step 2 (per batch of objects): conditional-BN tables (tiny fp32 GEMMs)
  *   c (B,c_dim); gamma_w/beta_w (11,256,c_dim) and gamma_b/beta_b (11,256) = conv_gamma/conv_beta of
  *   [blocks.0.bn_0, blocks.0.bn_1, ..., blocks.4.bn_1, bn]; run_mean/run_var (11,256); eps;
@@ -153,26 +153,41 @@ int rfd_occupancy_bits(const float *logits, int B, int T, float threshold, uint3
  *      [11][128]{a0,a1,c0,c1} the tensor-core kernel stages in shared memory.
  * Step 3: logits (B,T) = decoder(p).  p is (B,T,3) with p_batch_stride = T*3 floats, or one shared
  *   (T,3) lattice for every object with p_batch_stride = 0.
- * nsplit = 1: bf16 operands, fp32 accumulation/residual (config 4).  nsplit = 3 (bf16x3) is reserved:
- * RFD_ERR_UNSUPPORTED_SIZE for now; the fp32-exact results come from rfd_onet_decode_f32. */
-size_t rfd_onet_packed_bytes(int nsplit);
+ * `mode` selects the tensor-core operand format (weights must have been packed with the same mode); accumulation, the
+ * residual stream, the conditional-BN affine, fc_p and fc_out are fp32 in every mode:
+ *   RFD_ONET_MODE_BF16  (1)  bf16 x bf16, one MMA per K step.  |dlogit| ~ 3e-3 on unit-scale logits.
+ *   RFD_ONET_MODE_F16   (2)  fp16 x fp16, one MMA per K step, same speed, 8x smaller rounding error (~4e-4): meets
+ *                            BASELINE config 4's 1e-3.  The default of the Python mirror and of bench.py.  Activations
+ *                            saturate at +-65504 (never reached after conditional BN in practice).
+ *   RFD_ONET_MODE_F16X3 (3)  split fp16: a_hi.w_hi + a_lo.w_hi + a_hi.w_lo, three MMAs per K step (~22 significant
+ *                            bits per operand): |dlogit| ~ 1e-6, meets the north star's 1e-4 ("exact" tensor-core mode).
+ * Anything else: RFD_ERR_INVALID_ARGUMENT. */
+#define RFD_ONET_MODE_BF16 1
+#define RFD_ONET_MODE_F16 2
+#define RFD_ONET_MODE_F16X3 3
+size_t rfd_onet_packed_bytes(int mode); /* 0 for an unknown mode */
 size_t rfd_onet_aff_floats(void);
-int rfd_onet_pack_weights(const float *fc_w, int nsplit, void *packed, void *stream);
+int rfd_onet_pack_weights(const float *fc_w, int mode, void *packed, void *stream);
 int rfd_onet_cbn_tables(const float *c, int B, int c_dim, const float *gamma_w, const float *gamma_b,
                         const float *beta_w, const float *beta_b, const float *run_mean, const float *run_var,
                         float eps, const float *fc_bias, const float *x_bias, float *aff, void *stream);
 int rfd_onet_decode(const float *p, long long p_batch_stride, int B, int T, const float *fc_p_w /*(256,3)*/,
-                    const void *packed, int nsplit, const float *aff, const float *fc_out_w /*(256)*/,
+                    const void *packed, int mode, const float *aff, const float *fc_out_w /*(256)*/,
                     float fc_out_b, float *logits, void *stream);
+/* tuning knob (process-wide, atomic): 1 = independent CTAs; 2 = CTA pairs (thread-block clusters) that share every
+ * weight stage through cp.async.bulk multicast, halving the L2 -> SM weight traffic.  Default: RFD_ONET_CLUSTER or 2. */
+int rfd_onet_decode_set_cluster(int cluster);
 /* fp32 CUDA-core implementation of the same decoder (exact path, slow): the 1e-4 parity claim, the
  * on-GPU yardstick for the tensor-core path, and the "fp32" row of the benchmark.
  * workspace: at least 2*256*T*4 bytes (one object); larger = more objects per pass. */
 int rfd_onet_decode_f32(const float *p, long long p_batch_stride, int B, int T, const float *fc_p_w,
                         const float *fc_w /*(10,256,256)*/, const float *aff, const float *fc_out_w,
                         float fc_out_b, float *logits, float *workspace, size_t workspace_bytes, void *stream);
-/* diagnostics: while `trace` (device, 2*10*16 unsigned long long) is non-NULL, rfd_onet_decode runs an instrumented
- * kernel whose CTA 0 records clock64() at the MMA/epilogue hand-off points of its first two tiles. */
-int rfd_onet_decode_set_trace(unsigned long long *trace);
+/* diagnostics: rfd_onet_decode (mode RFD_ONET_MODE_F16, independent CTAs) through an instrumented kernel whose CTA 0
+ * records clock64() at the MMA/epilogue hand-off points of its first two tiles into `trace` (device, 2*10*16 u64). */
+int rfd_onet_decode_traced(const float *p, long long p_batch_stride, int B, int T, const float *fc_p_w,
+                           const void *packed, int mode, const float *aff, const float *fc_out_w, float fc_out_b,
+                           float *logits, unsigned long long *trace, void *stream);
 /* tcgen05 plumbing self-test: D (128,256) f32 = bf16(A (128,64)) . bf16(B (256,64))^T */
 int rfd_umma_selftest(const float *A, const float *B, float *D, void *stream);
 /* same product with the A operand staged in tensor memory (tcgen05.st.16x128b + TS-mode tcgen05.mma) */

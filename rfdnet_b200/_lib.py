@@ -42,7 +42,8 @@ SIGNATURES = {
     "rfd_onet_cbn_tables": [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp],
     "rfd_onet_decode": [_vp, _ll, _i, _i, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp],
     "rfd_onet_decode_f32": [_vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _sz, _vp],
-    "rfd_onet_decode_set_trace": [_vp],
+    "rfd_onet_decode_set_cluster": [_i],
+    "rfd_onet_decode_traced": [_vp, _ll, _i, _i, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp],
     "rfd_umma_selftest": [_vp, _vp, _vp, _vp],
     "rfd_umma_selftest_ts": [_vp, _vp, _vp, _vp],
 }

@@ -35,6 +35,8 @@
 //   * fc_p (K = 3) and fc_out (N = 1) are evaluated in fp32 on the CUDA cores inside the same kernel.
 #include "common.cuh"
 #include "umma.cuh"
+#include <atomic>
+#include <cstdlib>
 
 namespace rfd {
 
@@ -43,14 +45,17 @@ constexpr int DEC_LAYERS = 10;
 constexpr int DEC_CBN = 11;
 constexpr int DEC_TILE_M = 128;
 constexpr int DEC_KP = 4;
-constexpr int DEC_PANEL_A = DEC_TILE_M * 128;   // 16384 B : 128 rows x 64 bf16
-constexpr int DEC_STAGE_B = DEC_H * 128;        // 32768 B : 256 rows x 64 bf16
-constexpr int DEC_NSTAGE = 4;
+constexpr int DEC_PANEL_A = DEC_TILE_M * 128;   // 16384 B : 128 rows x 64 16-bit elements
+constexpr int DEC_STAGE_B = DEC_H * 128;        // 32768 B : 256 rows x 64 16-bit elements
+// operand modes (rfdnet_b200.h RFD_ONET_MODE_*)
+constexpr int MODE_BF16 = 1;    // bf16 x bf16, one MMA per K step
+constexpr int MODE_F16 = 2;     // fp16 x fp16 (11 significant bits instead of 8), one MMA per K step
+constexpr int MODE_F16X3 = 3;   // split fp16: a_hi.w_hi + a_lo.w_hi + a_hi.w_lo  (~22 significant bits)
 // per-object record in global memory (rfd_onet_cbn_tables):
 //   [0, 5632)      plain   [11 layers][a: 256][c: 256]                      (fp32 path)
 //   [5632, 5888)   x_bias  [256]
 //   [5888, 11520)  paired  [11 layers][128 column pairs]{a0, a1, c0, c1}    (tensor-core path)
-// the tensor-core kernel bulk-copies [5632, 11520) = DEC_AFF_FLOATS floats per tile.
+// the tensor-core kernel stages [5632, 11520) = DEC_AFF_FLOATS floats per object.
 constexpr int DEC_PLAIN_FLOATS = DEC_CBN * 2 * DEC_H;         // 5632
 constexpr int DEC_AFF_FLOATS = DEC_H + DEC_CBN * 2 * DEC_H;   // 5888 floats staged in shared memory
 constexpr int DEC_AFF_BYTES = DEC_AFF_FLOATS * 4;             // 23552
@@ -58,35 +63,63 @@ constexpr int DEC_REC_FLOATS = DEC_PLAIN_FLOATS + DEC_AFF_FLOATS;  // 11520
 constexpr int DEC_EPI_WARPS = 16;               // 4 TMEM lane quarters x 4 column quarters of every 64-column panel
 constexpr int DEC_THREADS = 64 + 32 * DEC_EPI_WARPS;  // warp 0 producer, warp 1 MMA, warps 2.. epilogue
 constexpr int DEC_CW = 16;                      // columns of a panel owned by one epilogue warp
+constexpr int DEC_MAX_STAGES = 4;
 
-// shared memory map (offsets from a 1024-B aligned base)
+// shared memory map (offsets from a 1024-B aligned base).  Activation panels + weight ring always fill 192 KB:
+//   one-MMA modes : A 64 KB                | 4-stage weight ring 128 KB
+//   MODE_F16X3    : A_hi 64 KB, A_lo 64 KB | 2-stage weight ring  64 KB
 constexpr int SM_AH = 0;
-constexpr int SM_W = SM_AH + DEC_KP * DEC_PANEL_A;              // 65536
-constexpr int SM_AFF = SM_W + DEC_NSTAGE * DEC_STAGE_B;         // 163840
+constexpr int SM_AL = DEC_KP * DEC_PANEL_A;                     // MODE_F16X3 only
+constexpr int SM_AFF = 6 * DEC_STAGE_B;                         // 196608
 constexpr int SM_WP = SM_AFF + DEC_AFF_BYTES;                   // single affine buffer (reloaded on object change)
-constexpr int SM_WOUT = SM_WP + 3 * DEC_H * 4;                  // 214016
-constexpr int SM_OUT = SM_WOUT + DEC_H * 4;                     // 215040
-constexpr int SM_BAR = SM_OUT + 4 * DEC_TILE_M * 4;             // 217088
-constexpr int SM_TOTAL = SM_BAR + 256;                          // 216320
+constexpr int SM_WOUT = SM_WP + 3 * DEC_H * 4;
+constexpr int SM_OUT = SM_WOUT + DEC_H * 4;
+constexpr int SM_BAR = SM_OUT + 4 * DEC_TILE_M * 4;
+constexpr int SM_TOTAL = SM_BAR + 256;
 constexpr int DEC_SMEM_BYTES = SM_TOTAL + 1024;                 // + alignment slack
+static_assert(DEC_SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 
 struct DecBars {
-  uint64_t w_full[DEC_NSTAGE];
-  uint64_t w_empty[DEC_NSTAGE];
-  uint64_t a_ready[DEC_KP];
+  uint64_t w_full[DEC_MAX_STAGES];
+  uint64_t w_empty[DEC_MAX_STAGES];
   uint64_t acc_ready;
   uint32_t tmem_base;
 };
 
-// TRACE: CTA 0 records clock64() at the hand-off points of its first two tiles (diagnostics, rfd_onet_decode_trace):
+// epilogue value pair -> operand panel(s): relu, round, store.  MODE_F16X3 also stores the rounding residual
+// (exact in fp32: lo = relu(v) - float(hi)) into the lo panel 64 KB above.
+template <int MODE>
+__device__ __forceinline__ void store_act_pair(uint32_t addr, float v0, float v1) {
+  if (MODE == MODE_BF16) {
+    umma::sts_u32(addr, umma::pack_relu_bf16x2(v0, v1));
+  } else {
+    const uint32_t h = umma::pack_relu_f16x2(v0, v1);
+    umma::sts_u32(addr, h);
+    if (MODE == MODE_F16X3) {
+      const float2 hf = umma::unpack_f16x2(h);
+      umma::sts_u32(addr + SM_AL, umma::pack_f16x2(fmaxf(v0, 0.f) - hf.x, fmaxf(v1, 0.f) - hf.y));
+    }
+  }
+}
+
+// TRACE: CTA 0 records clock64() at the hand-off points of its first two tiles (diagnostics, rfd_onet_decode_traced):
 //   trace[tile][layer][0..3] MMA thread: operands of panel kp ready ; [4..7] MMAs of panel kp issued + committed
-//   trace[tile][layer][8]    epilogue warp 2: acc_ready observed     ; [9..12] panel kp published (a_ready arrive)
-template <bool TRACE>
+//   trace[tile][layer][8]    epilogue warp 2: acc_ready observed     ; [9..12] panel kp published (named barrier arrive)
+//
+// CL (cluster size 1 or 2): with CL = 2 the two CTAs of a cluster stream the SAME weight stages; each CTA fetches one
+// 16-KB half of every stage from L2 and MULTICASTS it into both CTAs' rings (cp.async.bulk ... .multicast::cluster), so
+// every weight byte crosses the L2 -> SM fabric once per pair instead of once per CTA.  A ring slot is refilled only
+// when both CTAs' MMAs have retired it (tcgen05.commit ... .multicast::cluster arrives on both CTAs' w_empty barrier,
+// which therefore counts CL arrivals).  Everything else (TMEM, activation panels, hand-offs) stays CTA-local.
+template <int MODE, int CL, bool TRACE>
 __global__ void __launch_bounds__(DEC_THREADS, 1)
 onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const float *__restrict__ fc_p_w,
                    const uint8_t *__restrict__ packed, const float *__restrict__ aff_all,
                    const float *__restrict__ fc_out_w, float fc_out_b, float *__restrict__ logits, int num_tiles,
                    int tiles_per_obj, unsigned long long *__restrict__ trace) {
+  constexpr int NSTAGE = MODE == MODE_F16X3 ? 2 : 4;
+  constexpr int SPK = MODE == MODE_F16X3 ? 2 : 1;  // weight stages per (layer, k-panel): hi [, lo]
+  constexpr int SM_W = MODE == MODE_F16X3 ? 2 * DEC_KP * DEC_PANEL_A : DEC_KP * DEC_PANEL_A;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *s_ah = smem + SM_AH;
@@ -98,10 +131,10 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
   DecBars *bars = reinterpret_cast<DecBars *>(smem + SM_BAR);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t crank = CL > 1 ? umma::cluster_ctarank() : 0u;
 
   if (tid == 0) {
-    for (int i = 0; i < DEC_NSTAGE; ++i) { umma::mbar_init(&bars->w_full[i], 1); umma::mbar_init(&bars->w_empty[i], 1); }
-    for (int i = 0; i < DEC_KP; ++i) umma::mbar_init(&bars->a_ready[i], DEC_EPI_WARPS);
+    for (int i = 0; i < NSTAGE; ++i) { umma::mbar_init(&bars->w_full[i], 1); umma::mbar_init(&bars->w_empty[i], CL); }
     umma::mbar_init(&bars->acc_ready, 1);
     umma::fence_barrier_init();
   }
@@ -113,24 +146,36 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
   for (int e = tid; e < DEC_H; e += DEC_THREADS) s_wout[e] = __ldg(fc_out_w + e);
   umma::tc_fence_before();
   __syncthreads();
+  if (CL > 1) umma::cluster_sync();  // the peer's barriers exist before anything is multicast into this CTA
   umma::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   const uint32_t tmem_x = tmem_base, tmem_n = tmem_base + DEC_H;
-  // contiguous chunk of tiles per CTA: consecutive tiles of a CTA almost always belong to the same object, so the
-  // per-object affine table is (re)loaded only on an object change (2-3 times per launch)
-  const int tile_lo = (int)(((long long)num_tiles * blockIdx.x) / gridDim.x);
-  const int tile_hi = (int)(((long long)num_tiles * (blockIdx.x + 1)) / gridDim.x);
+  // contiguous chunk of tiles per cluster, dealt round-robin to its CTAs: consecutive tiles of a CTA almost always belong
+  // to the same object, so the per-object affine table is (re)loaded only on an object change (2-3 times per launch).
+  // Every CTA of a cluster runs the same number of weight passes (n_slots); a CTA without a tile in the last slot
+  // only drains the ring (phantom pass).
+  const int ncl = gridDim.x / CL, cid = blockIdx.x / CL;
+  const int c_lo = (int)(((long long)num_tiles * cid) / ncl);
+  const int c_hi = (int)(((long long)num_tiles * (cid + 1)) / ncl);
+  const int n_slots = (c_hi - c_lo + CL - 1) / CL;
+  const int tile0 = c_lo + (int)crank;
 
   if (warp == 0) {
     // ===================== producer: weight ring =====================
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
-      for (int tile = tile_lo; tile < tile_hi; ++tile) {
-        for (int s = 0; s < DEC_LAYERS * DEC_KP; ++s) {
+      for (int slot = 0; slot < n_slots; ++slot) {
+        for (int s = 0; s < DEC_LAYERS * DEC_KP * SPK; ++s) {
           umma::mbar_wait(&bars->w_empty[st], ph ^ 1u);
           umma::mbar_arrive_expect_tx(&bars->w_full[st], DEC_STAGE_B);
-          umma::bulk_g2s(s_w + st * DEC_STAGE_B, packed + (size_t)s * DEC_STAGE_B, DEC_STAGE_B, &bars->w_full[st]);
-          if (++st == DEC_NSTAGE) { st = 0; ph ^= 1u; }
+          if (CL == 1) {
+            umma::bulk_g2s(s_w + st * DEC_STAGE_B, packed + (size_t)s * DEC_STAGE_B, DEC_STAGE_B, &bars->w_full[st]);
+          } else {
+            constexpr uint32_t PART = DEC_STAGE_B / CL;
+            umma::bulk_g2s_multicast(s_w + st * DEC_STAGE_B + crank * PART, packed + (size_t)s * DEC_STAGE_B + crank * PART,
+                                     PART, &bars->w_full[st], (uint16_t)((1u << CL) - 1u));
+          }
+          if (++st == NSTAGE) { st = 0; ph ^= 1u; }
         }
       }
     }
@@ -141,37 +186,63 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
     // the last epilogue warp publishing a panel through an mbarrier and this thread resuming from try_wait; the
     // named barrier releases the waiting warp within tens of cycles.  MMA completion still uses tcgen05.commit ->
     // mbarrier (the only completion mechanism of the async tensor pipe).
-    {
-      constexpr uint32_t idesc = umma::make_idesc_bf16_f32(DEC_TILE_M, DEC_H);
-      const uint32_t ah_addr = umma::smem_u32(s_ah), w_addr = umma::smem_u32(s_w);
-      uint32_t st = 0, ph = 0, layer_count = 0;
-      for (int tile = tile_lo; tile < tile_hi; ++tile) {
-        for (int l = 0; l < DEC_LAYERS; ++l, ++layer_count) {
-          const uint32_t d = (l & 1) ? tmem_x : tmem_n;  // fc_0 -> net (fresh), fc_1 -> accumulate onto x
-          for (int kp = 0; kp < DEC_KP; ++kp) {
-            asm volatile("bar.sync %0, %1;" ::"r"(2 + kp), "n"(32 * DEC_EPI_WARPS + 32) : "memory");
-            if (lane == 0) {
+    constexpr uint32_t idesc = MODE == MODE_BF16 ? umma::make_idesc_bf16_f32(DEC_TILE_M, DEC_H)
+                                                 : umma::make_idesc_f16_f32(DEC_TILE_M, DEC_H);
+    const uint32_t ah_addr = umma::smem_u32(s_ah), w_addr = umma::smem_u32(s_w);
+    uint32_t st = 0, ph = 0;
+    for (int slot = 0; slot < n_slots; ++slot) {
+      const int tile = tile0 + slot * CL;
+      if (tile >= c_hi) {
+        // phantom pass (CL > 1 only): release every stage as soon as it has landed, MMA nothing
+        if (lane == 0) {
+          for (int s = 0; s < DEC_LAYERS * DEC_KP * SPK; ++s) {
+            umma::mbar_wait(&bars->w_full[st], ph);
+            for (uint32_t r = 0; r < (uint32_t)CL; ++r) umma::mbar_arrive_cluster(&bars->w_empty[st], r);
+            if (++st == NSTAGE) { st = 0; ph ^= 1u; }
+          }
+        }
+        __syncwarp();
+        continue;
+      }
+      const bool tr = TRACE && blockIdx.x == 0 && slot < 2;
+      for (int l = 0; l < DEC_LAYERS; ++l) {
+        const uint32_t d = (l & 1) ? tmem_x : tmem_n;  // fc_0 -> net (fresh), fc_1 -> accumulate onto x
+        for (int kp = 0; kp < DEC_KP; ++kp) {
+          asm volatile("bar.sync %0, %1;" ::"r"(2 + kp), "n"(32 * DEC_EPI_WARPS + 32) : "memory");
+          if (lane == 0) {
+#pragma unroll
+            for (int part = 0; part < SPK; ++part) {  // part 0: hi weights, part 1: lo weights
               umma::mbar_wait(&bars->w_full[st], ph);
               umma::tc_fence_after();
-              if (TRACE && blockIdx.x == 0 && tile - tile_lo < 2) trace[((tile - tile_lo) * DEC_LAYERS + l) * 16 + kp] = clock64();
+              if (tr && part == 0) trace[(slot * DEC_LAYERS + l) * 16 + kp] = clock64();
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t ad = umma::make_desc_k_sw128(ah_addr + kp * DEC_PANEL_A + k * 32);
                 const uint64_t bd = umma::make_desc_k_sw128(w_addr + st * DEC_STAGE_B + k * 32);
-                umma::mma_bf16_ss(d, ad, bd, idesc, (l & 1) ? 1u : (uint32_t)((kp | k) != 0));
+                umma::mma_f16_ss(d, ad, bd, idesc, (l & 1) ? 1u : (uint32_t)((kp | k | part) != 0));
               }
-              umma::mma_commit(&bars->w_empty[st]);  // frees the weight slot when these MMAs retire
-              if (kp == DEC_KP - 1) umma::mma_commit(&bars->acc_ready);
-              if (TRACE && blockIdx.x == 0 && tile - tile_lo < 2) trace[((tile - tile_lo) * DEC_LAYERS + l) * 16 + 4 + kp] = clock64();
+              if (MODE == MODE_F16X3 && part == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {  // a_lo . w_hi
+                  const uint64_t ad = umma::make_desc_k_sw128(ah_addr + SM_AL + kp * DEC_PANEL_A + k * 32);
+                  const uint64_t bd = umma::make_desc_k_sw128(w_addr + st * DEC_STAGE_B + k * 32);
+                  umma::mma_f16_ss(d, ad, bd, idesc, 1u);
+                }
+              }
+              // frees the weight slot (in every CTA of the cluster) when these MMAs retire
+              if (CL == 1) umma::mma_commit(&bars->w_empty[st]);
+              else umma::mma_commit_multicast(&bars->w_empty[st], (uint16_t)((1u << CL) - 1u));
+              if (++st == NSTAGE) { st = 0; ph ^= 1u; }
             }
-            __syncwarp();
-            if (++st == DEC_NSTAGE) { st = 0; ph ^= 1u; }
+            if (kp == DEC_KP - 1) umma::mma_commit(&bars->acc_ready);
+            if (tr) trace[(slot * DEC_LAYERS + l) * 16 + 4 + kp] = clock64();
           }
+          __syncwarp();
         }
       }
     }
   } else {
-    // ===================== epilogue warps (16): TMEM -> affine+ReLU -> bf16 A panels =====================
+    // ===================== epilogue warps (16): TMEM -> affine+ReLU -> 16-bit A panels =====================
     // TMEM is read with the 16x256b shape: a thread then owns 4 ROWS x (2 adjacent columns per 8-column block), so
     // one per-channel (a,c) fetch from shared memory serves four rows and every shared-memory store of a warp is a
     // conflict-free 128-byte wavefront (8 rows x 16 B after the 128B swizzle).  16 warps (4 per scheduler) hide the
@@ -185,7 +256,9 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint32_t layer_count = 0;
     int cur_obj = -1;
-    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+    for (int slot = 0; slot < n_slots; ++slot) {
+      const int tile = tile0 + slot * CL;
+      if (tile >= c_hi) break;
       const int obj = tile / tiles_per_obj;
       const int t0 = (tile - obj * tiles_per_obj) * DEC_TILE_M + q * 32 + lr;  // row j of this thread: t0 + 8j
       if (obj != cur_obj) {
@@ -234,8 +307,7 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
               x0 = fmaf(pz[j], w2.x, x0); x1 = fmaf(pz[j], w2.y, x1);
               v[j >> 1][4 * i + 2 * (j & 1)] = __float_as_uint(x0);
               v[j >> 1][4 * i + 2 * (j & 1) + 1] = __float_as_uint(x1);
-              umma::sts_u32(pan0 + kp * DEC_PANEL_A + j * 1024 + sw,
-                            umma::pack_relu_bf16x2(fmaf(x0, ac.x, ac.z), fmaf(x1, ac.y, ac.w)));
+              store_act_pair<MODE>(pan0 + kp * DEC_PANEL_A + j * 1024 + sw, fmaf(x0, ac.x, ac.z), fmaf(x1, ac.y, ac.w));
             }
           }
           umma::tmem_st_16x256b_x2(tmem_x + lane_base + cb, v[0]);
@@ -254,8 +326,8 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
         const float4 pre1 = umma::lds_f4(affi_a + (l + 1) * (DEC_H * 2 * 4) + cq * (DEC_CW / 2) * 16 + 64);
         umma::mbar_wait(&bars->acc_ready, layer_count & 1u);
         umma::tc_fence_after();
-        const bool tr = TRACE && blockIdx.x == 0 && tile - tile_lo < 2 && warp == 2 && lane == 0;
-        if (tr) trace[((tile - tile_lo) * DEC_LAYERS + l) * 16 + 8] = clock64();
+        const bool tr = TRACE && blockIdx.x == 0 && slot < 2 && warp == 2 && lane == 0;
+        if (tr) trace[(slot * DEC_LAYERS + l) * 16 + 8] = clock64();
         const uint32_t src = ((l & 1) ? tmem_x : tmem_n) + lane_base + cq * DEC_CW;
         const uint32_t al = affi_a + (l + 1) * (DEC_H * 2 * 4) + cq * (DEC_CW / 2) * 16;  // + kp*512 + i*64
         // software pipeline over the four panels: the TMEM load of panel kp+1 is in flight while panel kp is
@@ -268,7 +340,7 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
           for (int kp = 0; kp < DEC_KP; ++kp) {
             const float4 ac0 = kp ? umma::lds_f4(al + kp * 512) : pre0, ac1 = kp ? umma::lds_f4(al + kp * 512 + 64) : pre1;
             umma::tc_wait_ld();
-            if (tr && kp == 0) trace[((tile - tile_lo) * DEC_LAYERS + l) * 16 + 13] = clock64();
+            if (tr && kp == 0) trace[(slot * DEC_LAYERS + l) * 16 + 13] = clock64();
             if (kp + 1 < DEC_KP) {
               umma::tmem_ld_16x256b_x2(src + (kp + 1) * 64, v[(kp + 1) & 1][0]);
               umma::tmem_ld_16x256b_x2(src + (16u << 16) + (kp + 1) * 64, v[(kp + 1) & 1][1]);
@@ -282,15 +354,15 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
               for (int j = 0; j < 4; ++j) {
                 const float x0 = __uint_as_float(v[kp & 1][j >> 1][4 * i + 2 * (j & 1)]);
                 const float x1 = __uint_as_float(v[kp & 1][j >> 1][4 * i + 2 * (j & 1) + 1]);
-                umma::sts_u32(pan + j * 1024 + sw, umma::pack_relu_bf16x2(fmaf(x0, ac.x, ac.z), fmaf(x1, ac.y, ac.w)));
+                store_act_pair<MODE>(pan + j * 1024 + sw, fmaf(x0, ac.x, ac.z), fmaf(x1, ac.y, ac.w));
               }
             }
-            if (tr && kp == 0) trace[((tile - tile_lo) * DEC_LAYERS + l) * 16 + 14] = clock64();
+            if (tr && kp == 0) trace[(slot * DEC_LAYERS + l) * 16 + 14] = clock64();
             umma::fence_proxy_async_smem();
-            if (tr && kp == 0) trace[((tile - tile_lo) * DEC_LAYERS + l) * 16 + 15] = clock64();
+            if (tr && kp == 0) trace[(slot * DEC_LAYERS + l) * 16 + 15] = clock64();
             umma::tc_fence_before();
             asm volatile("bar.arrive %0, %1;" ::"r"(2 + kp), "n"(32 * DEC_EPI_WARPS + 32) : "memory");
-            if (tr) trace[((tile - tile_lo) * DEC_LAYERS + l) * 16 + 9 + kp] = clock64();
+            if (tr) trace[(slot * DEC_LAYERS + l) * 16 + 9 + kp] = clock64();
           }
         } else {
           // final: logits = fc_out(relu(cbn(x)))  -- fp32 dot product over the 256 channels
@@ -339,6 +411,7 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
   }
   umma::tc_fence_before();
   __syncthreads();
+  if (CL > 1) umma::cluster_sync();  // no CTA exits while a peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     umma::tc_fence_after();
     umma::tmem_dealloc(tmem_base, 512);
@@ -348,6 +421,8 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
 // ------------------------------------------------------------------------------------------------
 // weight packing: fc_w (10,256,256) f32 [layer][out n][in k]  ->  bf16, per (layer, k-panel) a 32-KB image of the
 // [256 rows n][64 k] K-major SWIZZLE_128B operand, stages in consumption order.
+// MODE_F16X3: two stages per (layer, k-panel): hi = fp16(w), lo = fp16(w - hi).
+template <int MODE>
 __global__ void onet_pack_kernel(const float *__restrict__ fc_w, uint8_t *__restrict__ packed) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 8 consecutive k (16 bytes)
   const int total = DEC_LAYERS * DEC_H * (DEC_H / 8);
@@ -356,11 +431,21 @@ __global__ void onet_pack_kernel(const float *__restrict__ fc_w, uint8_t *__rest
   const int n = rem / 32, kc = rem % 32;  // kc: 16-byte chunk index along k (0..31)
   const int kp = kc / 8, cin = kc % 8;
   const float *src = fc_w + ((size_t)l * DEC_H + n) * DEC_H + kc * 8;
-  uint32_t w[4];
+  constexpr int SPK = MODE == MODE_F16X3 ? 2 : 1;
+  uint32_t w[4], wl[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) w[i] = umma::pack_bf16x2(src[2 * i], src[2 * i + 1]);
-  uint8_t *dst = packed + (size_t)(l * DEC_KP + kp) * DEC_STAGE_B + n * 128 + ((cin ^ (n & 7)) << 4);
+  for (int i = 0; i < 4; ++i) {
+    if (MODE == MODE_BF16) {
+      w[i] = umma::pack_bf16x2(src[2 * i], src[2 * i + 1]);
+    } else {
+      w[i] = umma::pack_f16x2(src[2 * i], src[2 * i + 1]);
+      const float2 hf = umma::unpack_f16x2(w[i]);
+      wl[i] = umma::pack_f16x2(src[2 * i] - hf.x, src[2 * i + 1] - hf.y);
+    }
+  }
+  uint8_t *dst = packed + (size_t)((l * DEC_KP + kp) * SPK) * DEC_STAGE_B + n * 128 + ((cin ^ (n & 7)) << 4);
   *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+  if (MODE == MODE_F16X3) *reinterpret_cast<uint4 *>(dst + DEC_STAGE_B) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -590,17 +675,23 @@ extern "C" int rfd_umma_selftest_ts(const float *A, const float *Bm, float *D, v
   return RFD_OK;
 }
 
-extern "C" size_t rfd_onet_packed_bytes(int nsplit) {
-  return nsplit == 1 ? (size_t)DEC_LAYERS * DEC_KP * DEC_STAGE_B : 0;
+static bool valid_mode(int mode) { return mode == MODE_BF16 || mode == MODE_F16 || mode == MODE_F16X3; }
+
+extern "C" size_t rfd_onet_packed_bytes(int mode) {
+  if (!valid_mode(mode)) return 0;
+  return (size_t)DEC_LAYERS * DEC_KP * DEC_STAGE_B * (mode == MODE_F16X3 ? 2 : 1);
 }
 
 extern "C" size_t rfd_onet_aff_floats(void) { return DEC_REC_FLOATS; }
 
-extern "C" int rfd_onet_pack_weights(const float *fc_w, int nsplit, void *packed, void *stream) {
-  if (!fc_w || !packed) return RFD_ERR_INVALID_ARGUMENT;
-  if (nsplit != 1) return RFD_ERR_UNSUPPORTED_SIZE;
+extern "C" int rfd_onet_pack_weights(const float *fc_w, int mode, void *packed, void *stream) {
+  if (!fc_w || !packed || !valid_mode(mode)) return RFD_ERR_INVALID_ARGUMENT;
   const int total = DEC_LAYERS * DEC_H * (DEC_H / 8);
-  onet_pack_kernel<<<h_ceil_div(total, 256), 256, 0, as_stream(stream)>>>(fc_w, reinterpret_cast<uint8_t *>(packed));
+  const int grid = h_ceil_div(total, 256);
+  uint8_t *dst = reinterpret_cast<uint8_t *>(packed);
+  if (mode == MODE_BF16) onet_pack_kernel<MODE_BF16><<<grid, 256, 0, as_stream(stream)>>>(fc_w, dst);
+  else if (mode == MODE_F16) onet_pack_kernel<MODE_F16><<<grid, 256, 0, as_stream(stream)>>>(fc_w, dst);
+  else onet_pack_kernel<MODE_F16X3><<<grid, 256, 0, as_stream(stream)>>>(fc_w, dst);
   RFD_CHECK_LAUNCH("onet_pack_kernel");
   return RFD_OK;
 }
@@ -625,43 +716,97 @@ extern "C" int rfd_onet_cbn_tables(const float *c, int B, int c_dim, const float
   return RFD_OK;
 }
 
-static unsigned long long *g_decode_trace = nullptr;
+// weight-sharing cluster size of the tensor-core decoder (1 = independent CTAs, 2 = CTA pairs with multicast weight
+// stages).  Process-wide tuning knob; the default comes from RFD_ONET_CLUSTER (else DEC_DEFAULT_CLUSTER).
+constexpr int DEC_DEFAULT_CLUSTER = 2;
+static std::atomic<int> g_decode_cluster{0};
 
-extern "C" int rfd_onet_decode(const float *p, long long p_batch_stride, int B, int T, const float *fc_p_w,
-                               const void *packed, int nsplit, const float *aff, const float *fc_out_w,
-                               float fc_out_b, float *logits, void *stream) {
+static int decode_cluster() {
+  int c = g_decode_cluster.load(std::memory_order_relaxed);
+  if (c == 0) {
+    const char *e = getenv("RFD_ONET_CLUSTER");
+    c = (e && (e[0] == '1' || e[0] == '2') && e[1] == 0) ? e[0] - '0' : DEC_DEFAULT_CLUSTER;
+    g_decode_cluster.store(c, std::memory_order_relaxed);
+  }
+  return c;
+}
+
+extern "C" int rfd_onet_decode_set_cluster(int cluster) {
+  if (cluster != 1 && cluster != 2) return RFD_ERR_INVALID_ARGUMENT;
+  g_decode_cluster.store(cluster, std::memory_order_relaxed);
+  return RFD_OK;
+}
+
+template <int MODE, int CL, bool TRACE>
+static int launch_decode_t(const float *p, long long p_stride, int T, const float *fc_p_w, const uint8_t *packed,
+                           const float *aff, const float *fc_out_w, float fc_out_b, float *logits, int num_tiles,
+                           int tiles_per_obj, unsigned long long *trace, int sms, cudaStream_t st) {
+  auto kern = onet_decode_kernel<MODE, CL, TRACE>;
+  RFD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES), "decode attr");
+  int grid = num_tiles < sms ? num_tiles : sms;
+  grid = (grid / CL) * CL;  // whole clusters (CL > 1 callers guarantee num_tiles >= CL)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(DEC_THREADS);
+  cfg.dynamicSmemBytes = DEC_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RFD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p, p_stride, T, fc_p_w, packed, aff, fc_out_w, fc_out_b, logits, num_tiles,
+                                    tiles_per_obj, trace),
+                 "onet_decode_kernel launch");
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return RFD_OK;
+}
+
+static int launch_decode(const float *p, long long p_batch_stride, int B, int T, const float *fc_p_w, const void *packed,
+                         int mode, const float *aff, const float *fc_out_w, float fc_out_b, float *logits,
+                         unsigned long long *trace, void *stream) {
   if (B < 0 || T < 0 || p_batch_stride < 0) return RFD_ERR_INVALID_ARGUMENT;
+  if (!valid_mode(mode)) return RFD_ERR_INVALID_ARGUMENT;
   if (B == 0 || T == 0) return RFD_OK;
   if (!p || !fc_p_w || !packed || !aff || !fc_out_w || !logits) return RFD_ERR_INVALID_ARGUMENT;
-  if (nsplit != 1) return RFD_ERR_UNSUPPORTED_SIZE;
   const long long tiles_per_obj = (T + DEC_TILE_M - 1) / DEC_TILE_M;
   const long long num_tiles = tiles_per_obj * B;
   if (num_tiles > 0x7fffffffLL) return RFD_ERR_UNSUPPORTED_SIZE;
   int dev = 0, sms = 148;
   RFD_CHECK_CUDA(cudaGetDevice(&dev), "decode getdevice");
   RFD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "decode sms");
-  const int grid = (int)(num_tiles < sms ? num_tiles : sms);
-  if (g_decode_trace) {
-    RFD_CHECK_CUDA(cudaFuncSetAttribute(onet_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES),
-                   "decode attr");
-    onet_decode_kernel<true><<<grid, DEC_THREADS, DEC_SMEM_BYTES, as_stream(stream)>>>(
-        p, p_batch_stride, T, fc_p_w, reinterpret_cast<const uint8_t *>(packed), aff, fc_out_w, fc_out_b, logits,
-        (int)num_tiles, (int)tiles_per_obj, g_decode_trace);
-  } else {
-    RFD_CHECK_CUDA(cudaFuncSetAttribute(onet_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES),
-                   "decode attr");
-    onet_decode_kernel<false><<<grid, DEC_THREADS, DEC_SMEM_BYTES, as_stream(stream)>>>(
-        p, p_batch_stride, T, fc_p_w, reinterpret_cast<const uint8_t *>(packed), aff, fc_out_w, fc_out_b, logits,
-        (int)num_tiles, (int)tiles_per_obj, nullptr);
+  const uint8_t *pk = reinterpret_cast<const uint8_t *>(packed);
+  cudaStream_t st = as_stream(stream);
+  const int nt = (int)num_tiles, tpo = (int)tiles_per_obj;
+  const int cl = (num_tiles >= 2 && !trace) ? decode_cluster() : 1;
+#define RFD_DEC_LAUNCH(M, C, TR) \
+  return launch_decode_t<M, C, TR>(p, p_batch_stride, T, fc_p_w, pk, aff, fc_out_w, fc_out_b, logits, nt, tpo, trace, sms, st)
+  if (trace) {
+    if (mode != MODE_F16) return RFD_ERR_INVALID_ARGUMENT;  // the instrumented instantiation exists for the default mode
+    RFD_DEC_LAUNCH(MODE_F16, 1, true);
   }
-  RFD_CHECK_LAUNCH("onet_decode_kernel");
-  return RFD_OK;
+  if (mode == MODE_BF16) { if (cl == 2) RFD_DEC_LAUNCH(MODE_BF16, 2, false); RFD_DEC_LAUNCH(MODE_BF16, 1, false); }
+  if (mode == MODE_F16) { if (cl == 2) RFD_DEC_LAUNCH(MODE_F16, 2, false); RFD_DEC_LAUNCH(MODE_F16, 1, false); }
+  if (cl == 2) RFD_DEC_LAUNCH(MODE_F16X3, 2, false);
+  RFD_DEC_LAUNCH(MODE_F16X3, 1, false);
+#undef RFD_DEC_LAUNCH
 }
 
-// diagnostics: the next rfd_onet_decode calls record the hand-off timeline of CTA 0 into trace (2*10*16 u64); NULL = off
-extern "C" int rfd_onet_decode_set_trace(unsigned long long *trace) {
-  g_decode_trace = trace;
-  return RFD_OK;
+extern "C" int rfd_onet_decode(const float *p, long long p_batch_stride, int B, int T, const float *fc_p_w,
+                               const void *packed, int mode, const float *aff, const float *fc_out_w,
+                               float fc_out_b, float *logits, void *stream) {
+  return launch_decode(p, p_batch_stride, B, T, fc_p_w, packed, mode, aff, fc_out_w, fc_out_b, logits, nullptr, stream);
+}
+
+// diagnostics: the same decode with an instrumented kernel (RFD_ONET_MODE_F16, cluster 1) whose CTA 0 records the hand-off
+// timeline of its first two tiles into trace (device, 2*10*16 u64).  The trace buffer is an argument, not process state.
+extern "C" int rfd_onet_decode_traced(const float *p, long long p_batch_stride, int B, int T, const float *fc_p_w,
+                                      const void *packed, int mode, const float *aff, const float *fc_out_w,
+                                      float fc_out_b, float *logits, unsigned long long *trace, void *stream) {
+  if (!trace) return RFD_ERR_INVALID_ARGUMENT;
+  return launch_decode(p, p_batch_stride, B, T, fc_p_w, packed, mode, aff, fc_out_w, fc_out_b, logits, trace, stream);
 }
 
 extern "C" int rfd_onet_decode_f32(const float *p, long long p_batch_stride, int B, int T, const float *fc_p_w,

@@ -8,8 +8,9 @@ generator.py:91-97,123-143 (dense 32^3 query, eval_points).
 fc_p.weight (256,3,1), fc_z.weight (256,z), blocks.{i}.bn_{0,1}.conv_{gamma,beta}.weight (256,c,1),
 blocks.{i}.bn_{0,1}.bn.running_{mean,var}, blocks.{i}.fc_{0,1}.weight (256,256,1), bn.*, fc_out.weight (1,256,1)).
 forward(p, z, c) -> logits (B,T):
-  * eval mode, CUDA, no autograd: one persistent tcgen05 kernel (precision='bf16') or the fp32 CUDA-core
-    path (precision='fp32');
+  * eval mode, CUDA, no autograd: one persistent tcgen05 kernel -- precision 'fp16' (default; |dlogit| ~ 4e-4,
+    BASELINE config 4's 1e-3), 'fp16x3' (split-fp16, three MMAs per K step, |dlogit| ~ 1e-6: the north star's 1e-4
+    on tensor cores), 'bf16' (legacy, ~3e-3) -- or the fp32 CUDA-core path (precision='fp32');
   * otherwise (training / batch-statistics CBN): the reference's op sequence in PyTorch.
 """
 import torch
@@ -74,7 +75,7 @@ class DecoderCBatchNorm(nn.Module):
     """occ_decoder.py:72-122"""
 
     def __init__(self, dim=3, z_dim=128, c_dim=128, hidden_size=256, n_blocks=5, leaky=False, legacy=False,
-                 precision='bf16'):
+                 precision='fp16'):
         super().__init__()
         assert not leaky and not legacy
         self.z_dim, self.c_dim, self.hidden_size, self.n_blocks = z_dim, c_dim, hidden_size, n_blocks
@@ -87,18 +88,19 @@ class DecoderCBatchNorm(nn.Module):
         self.actvn = nn.ReLU()
         self.precision = precision
         self._packed = None
+        self._packed_tc = {}
 
     # -- cache invalidation
     def train(self, mode=True):
-        self._packed = None
+        self._packed, self._packed_tc = None, {}
         return super().train(mode)
 
     def _load_from_state_dict(self, *a, **k):
-        self._packed = None
+        self._packed, self._packed_tc = None, {}
         return super()._load_from_state_dict(*a, **k)
 
     def _apply(self, fn, *a, **k):
-        self._packed = None
+        self._packed, self._packed_tc = None, {}
         return super()._apply(fn, *a, **k)
 
     def _cbn_layers(self):
@@ -115,8 +117,10 @@ class DecoderCBatchNorm(nn.Module):
 
     def pack(self):
         """Gather the parameters into the flat device arrays the C ABI takes (cached until the weights change)."""
-        if self._packed is not None:
+        ver = self._param_version()
+        if self._packed is not None and self._packed['version'] == ver:
             return self._packed
+        self._packed_tc = {}
         assert self.hidden_size == 256 and self.n_blocks == 5, "kernel is built for hidden 256, 5 blocks"
         lib = _lib.load()
         cbn, fcs = self._cbn_layers(), self._fc_layers()
@@ -136,13 +140,32 @@ class DecoderCBatchNorm(nn.Module):
             'fc_out_w': f32(self.fc_out.weight).view(256).contiguous(),
             'fc_out_b': float(self.fc_out.bias.detach().float().item()),
         }
-        nbytes = lib.rfd_onet_packed_bytes(1)
-        P['packed'] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
-            _lib.check(lib.rfd_onet_pack_weights(P['fc_w'].data_ptr(), 1, P['packed'].data_ptr(),
-                                                 torch.cuda.current_stream().cuda_stream), "onet_pack_weights")
+        P['version'] = ver
         self._packed = P
         return P
+
+    def _param_version(self):
+        """Changes whenever a parameter / buffer is modified in place or replaced (tensor._version + storage address):
+        the folded tables are re-derived instead of silently going stale (fine-tuning in eval(), manual edits)."""
+        v = 0
+        for t in list(self.parameters()) + list(self.buffers()):
+            v = (v * 1000003 + t._version * 7919 + t.data_ptr()) & 0xFFFFFFFFFFFF
+        return v
+
+    MODES = {'bf16': 1, 'fp16': 2, 'fp16x3': 3}
+
+    def packed_tc(self, precision):
+        """Swizzled 16-bit operand images of the ten 256x256 fc weights for one tensor-core mode."""
+        P = self.pack()
+        if precision not in self._packed_tc:
+            lib = _lib.load()
+            mode = self.MODES[precision]
+            buf = torch.empty(lib.rfd_onet_packed_bytes(mode), dtype=torch.uint8, device=P['fc_w'].device)
+            with torch.cuda.device(buf.device):
+                _lib.check(lib.rfd_onet_pack_weights(P['fc_w'].data_ptr(), mode, buf.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream), "onet_pack_weights")
+            self._packed_tc[precision] = buf
+        return self._packed_tc[precision]
 
     def cbn_tables(self, z, c):
         """(B, aff_floats) per-object affine tables + x_bias (rfd_onet_cbn_tables)."""
@@ -180,12 +203,15 @@ class DecoderCBatchNorm(nn.Module):
         logits = torch.empty((B, T), dtype=torch.float32, device=c.device)
         with torch.cuda.device(c.device):
             st = torch.cuda.current_stream().cuda_stream
-            if precision == 'bf16':
-              # algorithmic FLOP: 2*(3*256 + 10*256*256 + 256) per query point
-              with _lib.timed("onet_decode", float(B) * T * 1312768.0):
-                _lib.check(lib.rfd_onet_decode(p.data_ptr(), stride, B, T, P['fc_p_w'].data_ptr(),
-                                               P['packed'].data_ptr(), 1, aff.data_ptr(), P['fc_out_w'].data_ptr(),
-                                               P['fc_out_b'], logits.data_ptr(), st), "onet_decode")
+            if precision in self.MODES:
+                packed = self.packed_tc(precision)
+                # algorithmic FLOP: 2*(3*256 + 10*256*256 + 256) per query point (fp16x3 issues 3x the
+                # tensor-core work for the same algorithmic FLOP)
+                with _lib.timed("onet_decode", float(B) * T * 1312768.0):
+                    _lib.check(lib.rfd_onet_decode(p.data_ptr(), stride, B, T, P['fc_p_w'].data_ptr(),
+                                                   packed.data_ptr(), self.MODES[precision], aff.data_ptr(),
+                                                   P['fc_out_w'].data_ptr(), P['fc_out_b'], logits.data_ptr(), st),
+                               "onet_decode")
             elif precision == 'fp32':
                 per_obj = 2 * 256 * T * 4
                 nobj = max(1, min(B, workspace_bytes // per_obj))
@@ -196,6 +222,22 @@ class DecoderCBatchNorm(nn.Module):
                                                    st), "onet_decode_f32")
             else:
                 raise ValueError(precision)
+        return logits
+
+    def decode_traced(self, p, z, c, trace):
+        """Diagnostics (tools/trace_decoder.py): decode in the default fp16 mode through the instrumented kernel;
+        `trace` = int64 cuda tensor of 2*10*16 entries receiving CTA 0's hand-off timeline."""
+        P, lib = self.pack(), _lib.load()
+        B, T = c.shape[0], p.shape[0]
+        assert p.dim() == 2 and trace.numel() >= 320 and trace.dtype == torch.int64
+        aff = self.cbn_tables(z, c)
+        logits = torch.empty((B, T), dtype=torch.float32, device=c.device)
+        with torch.cuda.device(c.device):
+            _lib.check(lib.rfd_onet_decode_traced(p.data_ptr(), 0, B, T, P['fc_p_w'].data_ptr(),
+                                                  self.packed_tc('fp16').data_ptr(), 2, aff.data_ptr(),
+                                                  P['fc_out_w'].data_ptr(), P['fc_out_b'], logits.data_ptr(),
+                                                  trace.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                       "onet_decode_traced")
         return logits
 
     def forward(self, p, z, c, **kwargs):

@@ -14,8 +14,8 @@ from . import detection, onet
 
 class SceneHotPath(nn.Module):
     def __init__(self, input_feature_dim=1, num_proposal=256, z_dim=32, c_dim=512, resolution=32, box_size=1.1,
-                 precision='bf16', backbone_precision='fp32', head_precision='bf16'):
-        """precision: ONet decoder ('bf16' tcgen05 | 'fp32').  backbone_precision: shared MLPs of SA1-4
+                 precision='fp16', backbone_precision='fp32', head_precision='bf16'):
+        """precision: ONet decoder ('fp16' | 'fp16x3' | 'bf16' tcgen05 modes, 'fp32' CUDA cores).  backbone_precision: shared MLPs of SA1-4
         (BASELINE config 2: fp32).  head_precision: shared MLP of the vote-aggregation SA layer (BASELINE config 3:
         bf16 tensor-core path)."""
         super().__init__()

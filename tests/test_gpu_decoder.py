@@ -1,5 +1,9 @@
-"""GPU tests of the ONet decoder: tcgen05 plumbing self-test, fp32 exact path (1e-4) and bf16 tensor-core path
-against the reference-generated golden logits / oracle/model_ref, plus full 32^3 properties."""
+"""GPU tests of the ONet decoder: tcgen05 plumbing self-test, fp32 exact path and the tensor-core modes against the
+reference-generated golden logits / oracle/model_ref, with the tolerances the contract states:
+  fp16 (default, benchmarked)  abs <= 1e-3   (BASELINE.json config 4)
+  fp16x3 (exact TC mode), fp32 abs <= 1e-4   (north star)
+  bf16 (legacy opt-in)         abs <= 1e-2   (not a conforming mode; documented, measured ~3e-3)
+plus the full 256 x 32^3 shape against the oracle on 8 whole objects."""
 import numpy as np
 import pytest
 import torch
@@ -11,8 +15,7 @@ from rfdnet_b200.synth import seeded_fill
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
-# bf16 operands through ten 256x256 layers: error budget relative to the logit scale (measured ~3e-3)
-BF16_REL_TOL = 2e-2
+TOL = {"fp16": 1e-3, "fp16x3": 1e-4, "fp32": 1e-4, "bf16": 1e-2}   # absolute, on logits of scale ~1
 
 
 def test_umma_selftest():
@@ -67,57 +70,99 @@ def test_decoder_fp32_path_vs_golden(golden):
     assert np.allclose(out_z.cpu().numpy(), golden["dec_logits_z"], atol=1e-4, rtol=1e-4)
 
 
-def test_decoder_bf16_tensor_core_path_vs_golden(golden):
+@pytest.mark.parametrize("precision", ["fp16", "fp16x3", "bf16"])
+def test_decoder_tensor_core_modes_vs_golden(golden, precision):
     dec = _decoder().to(DEV)
+    dec.precision = precision
     grid = onet.make_3d_grid(32, 1.1, DEV)
     p = grid[torch.from_numpy(golden["dec_sel"]).long().to(DEV)].contiguous()
     c = torch.from_numpy(golden["dec_c"]).to(DEV)
     with torch.no_grad():
         out = dec(p.unsqueeze(0).expand(3, -1, -1).contiguous(), torch.zeros(3, 32, device=DEV), c)  # module forward
-    ref = golden["dec_logits"]
-    err = np.abs(out.cpu().numpy() - ref).max()
-    scale = np.abs(ref).max()
-    print(f"bf16 decoder: max|err| {err:.4e}, logit scale {scale:.3f}, rel {err / scale:.3e}")
-    assert err <= BF16_REL_TOL * max(1.0, scale)
-    assert ((out.cpu().numpy() >= 0) == (ref >= 0)).mean() > 0.99  # occupancy decision (threshold logit(0.5) = 0)
+        out_z = dec(p.unsqueeze(0).expand(3, -1, -1).contiguous(), torch.from_numpy(golden["dec_z2"]).to(DEV), c)
+    for o, ref in ((out, golden["dec_logits"]), (out_z, golden["dec_logits_z"])):
+        err = np.abs(o.cpu().numpy() - ref).max()
+        print(f"{precision} decoder: max|err| {err:.3e}, logit scale {np.abs(ref).max():.3f}")
+        assert err <= TOL[precision], (precision, err)
+        assert ((o.cpu().numpy() >= 0) == (ref >= 0)).mean() > (0.999 if precision != "bf16" else 0.99)
 
 
-@pytest.mark.parametrize("B,T", [(1, 1), (2, 127), (3, 129), (5, 1000), (300, 256)])
-def test_decoder_bf16_vs_fp32_ragged_sizes(B, T):
+def test_default_mode_is_fp16():
+    assert onet.DecoderCBatchNorm(dim=3, z_dim=32, c_dim=512).precision == "fp16"
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 127), (3, 129), (5, 1000), (300, 256), (1, 128), (1, 129)])
+@pytest.mark.parametrize("cluster", [1, 2])
+def test_decoder_modes_vs_fp32_ragged_sizes(B, T, cluster):
+    """ragged tile counts: odd numbers of 128-point tiles exercise the phantom pass of the weight-sharing CTA pairs."""
+    lib = _lib.load()
     dec = _decoder(seed=7).to(DEV)
     g = torch.Generator(device="cpu").manual_seed(B * 1000 + T)
     p = (torch.rand(B, T, 3, generator=g) - 0.5).to(DEV)
     c = torch.randn(B, 512, generator=g).to(DEV)
     z = (torch.randn(B, 32, generator=g) * 0.2).to(DEV)
-    with torch.no_grad():
-        a = dec.decode(p, z, c, precision="fp32")
-        b = dec.decode(p, z, c, precision="bf16")
-    scale = float(a.abs().max())
-    assert float((a - b).abs().max()) <= BF16_REL_TOL * max(1.0, scale)
+    _lib.check(lib.rfd_onet_decode_set_cluster(cluster), "set_cluster")
+    try:
+        with torch.no_grad():
+            a = dec.decode(p, z, c, precision="fp32")
+            outs = {m: dec.decode(p, z, c, precision=m) for m in ("fp16", "fp16x3", "bf16")}
+        torch.cuda.synchronize()
+    finally:
+        lib.rfd_onet_decode_set_cluster(2)
+    for m, b in outs.items():
+        assert float((a - b).abs().max()) <= TOL[m], (m, float((a - b).abs().max()))
     if B <= 3:
         sd = {k: v.cpu() for k, v in dec.state_dict().items()}
         ref = model_ref.decoder(p.cpu(), z.cpu(), c.cpu(), sd)
-        assert torch.allclose(a.cpu(), ref, atol=1e-4, rtol=1e-4)
+        assert torch.allclose(a.cpu(), ref, atol=1e-4, rtol=0)
+        assert float((outs["fp16x3"].cpu() - ref).abs().max()) <= 1e-4
 
 
-def test_decoder_full_grid_properties():
-    """config 4 shape at reduced object count: 8 objects x 32^3 shared lattice.  Size-independent checks:
-    object independence (row b only depends on c[b]) and agreement with the fp32 path on a strided subset."""
+def test_decoder_cluster_modes_bitwise_equal():
+    """weight sharing changes where the operand bytes come from, not the arithmetic: cluster 1 == cluster 2 bit for bit"""
+    lib = _lib.load()
+    dec = _decoder(seed=11).to(DEV)
+    grid = onet.make_3d_grid(32, 1.1, DEV)
+    c = torch.randn(5, 512, generator=torch.Generator().manual_seed(2)).to(DEV)
+    z = torch.zeros(5, 32, device=DEV)
+    res = {}
+    try:
+        for cl in (1, 2):
+            _lib.check(lib.rfd_onet_decode_set_cluster(cl), "set_cluster")
+            with torch.no_grad():
+                res[cl] = [dec.decode(grid, z, c, precision=m) for m in ("fp16", "fp16x3")]
+    finally:
+        lib.rfd_onet_decode_set_cluster(2)
+    for a, b in zip(res[1], res[2]):
+        assert torch.equal(a, b)
+
+
+def test_decoder_full_shape_vs_oracle():
+    """BASELINE config 4 at its real shape: 256 objects x 32^3 shared lattice.  Eight whole objects (first, last and six
+    in between) are compared with the CPU oracle (oracle/model_ref.decoder, fp32): fp16 <= 1e-3, fp16x3 <= 1e-4."""
     dec = _decoder(seed=9).to(DEV)
     grid = onet.make_3d_grid(32, 1.1, DEV)
     g = torch.Generator().manual_seed(1)
-    c = torch.randn(8, 512, generator=g).to(DEV)
-    z = torch.zeros(8, 32, device=DEV)
+    c = torch.randn(256, 512, generator=g).to(DEV)
+    z = torch.zeros(256, 32, device=DEV)
+    pick = [0, 1, 37, 100, 127, 128, 200, 255]
     with torch.no_grad():
-        full = dec.decode(grid, z, c, precision="bf16")
-        assert full.shape == (8, 32768) and torch.isfinite(full).all()
-        perm = torch.tensor([3, 0, 7, 1, 2, 6, 5, 4], device=DEV)
-        full_p = dec.decode(grid, z, c[perm].contiguous(), precision="bf16")
-        assert torch.equal(full_p, full[perm])                       # per-object, bitwise deterministic
-        sub = grid[::37].contiguous()
-        ref = dec.decode(sub, z, c, precision="fp32")
+        full = {m: dec.decode(grid, z, c, precision=m) for m in ("fp16", "fp16x3")}
+        for m in full:
+            assert full[m].shape == (256, 32768) and torch.isfinite(full[m]).all()
+        # object independence + determinism: a permuted batch gives the permuted rows bit for bit
+        perm = torch.randperm(256, generator=g).to(DEV)
+        assert torch.equal(dec.decode(grid, z, c[perm].contiguous(), precision="fp16"), full["fp16"][perm])
+    sd = {k: v.cpu() for k, v in dec.state_dict().items()}
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    with torch.no_grad():
+        ref = model_ref.decoder(grid.cpu().unsqueeze(0).expand(len(pick), -1, -1), z[pick].cpu(), c[pick].cpu(), sd)
     scale = float(ref.abs().max())
-    assert float((full[:, ::37] - ref).abs().max()) <= BF16_REL_TOL * max(1.0, scale)
+    for m in full:
+        err = float((full[m][pick].cpu() - ref).abs().max())
+        print(f"256x32^3 {m}: max|err| vs oracle on 8 objects {err:.3e} (logit scale {scale:.2f})")
+        assert err <= TOL[m], (m, err)
+        assert ((full[m][pick].cpu() >= 0) == (ref >= 0)).float().mean() > 0.999
 
 
 @pytest.mark.parametrize("B,T", [(3, 32768), (5, 1000), (1, 1), (2, 33)])

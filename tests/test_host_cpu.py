@@ -25,13 +25,14 @@ def test_cabi_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/rfdnet_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.rfd_abi_version() == 1
+    assert lib.rfd_abi_version() == 2
     assert b"invalid" in lib.rfd_status_string(-1)
     # argument validation happens before any CUDA call, so it is testable without a GPU
     assert lib.rfd_furthest_point_sampling(None, 1, 0, 4, None, None) == -1
     assert lib.rfd_ball_query(None, None, 1, 10, 10, 0.1, 4, None, None) == -1
     assert lib.rfd_onet_decode(None, 0, 1, 128, None, None, 3, None, None, 0.0, None, None) == -1
-    assert lib.rfd_onet_packed_bytes(1) == 10 * 4 * 256 * 128
+    assert lib.rfd_onet_packed_bytes(1) == 10 * 4 * 256 * 128 == lib.rfd_onet_packed_bytes(2)
+    assert lib.rfd_onet_packed_bytes(3) == 2 * 10 * 4 * 256 * 128
     assert lib.rfd_onet_aff_floats() == 2 * 11 * 2 * 256 + 256
 
 
@@ -200,8 +201,9 @@ def test_c_abi_from_plain_c(lib, tmp_path):
     exe = tmp_path / "abi_check"
     libdir = os.path.dirname(_lib.LIB_PATH)
     cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "tests", "c", "abi_check.c"), "-o", str(exe), "-L", libdir, "-lrfdnet_b200",
-           "-Wl,-rpath," + libdir]
+           "-isystem", "/usr/local/cuda/include", os.path.join(ROOT, "tests", "c", "abi_check.c"), "-o", str(exe),
+           "-L", libdir, "-lrfdnet_b200", "-L", "/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir,
+           "-Wl,-rpath,/usr/local/cuda/lib64"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)

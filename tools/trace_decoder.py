@@ -11,12 +11,9 @@ c = torch.randn(256, 512, device=dev); z = torch.zeros(256, 32, device=dev)
 with torch.no_grad():
     dec.decode(grid, z, c)
 trace = torch.zeros(2 * 10 * 16, dtype=torch.int64, device=dev)
-lib = _lib.load()
-lib.rfd_onet_decode_set_trace(trace.data_ptr())
 with torch.no_grad():
-    dec.decode(grid, z, c)
+    dec.decode_traced(grid, z, c, trace)
 torch.cuda.synchronize()
-lib.rfd_onet_decode_set_trace(None)
 t = trace.cpu().view(2, 10, 16).numpy()
 tile = t[1]
 base = tile[0, 0]
