@@ -24,6 +24,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "scenes/sec (80k pts, 256 proposals, 32^3 occ queries)"
+WORKLOAD = "full hot path: 80k-pt scene -> backbone (4 SA + 2 FP) + vote + 256 proposals -> ONet decoder 256 x 32^3"
 FLOP_PER_POINT = 1312768.0
 
 
@@ -99,10 +100,11 @@ def bind_to_gpu_numa_node(index):
     return 0
 
 
-def build_model(device, seed=0, backbone_precision="fp32"):
+def build_model(device, seed=0, backbone_precision="x3", head_precision="x3", decoder_precision="fp16"):
     from rfdnet_b200.pipeline import SceneHotPath
     from rfdnet_b200.synth import seeded_fill
-    net = SceneHotPath(backbone_precision=backbone_precision).eval()
+    net = SceneHotPath(precision=decoder_precision, backbone_precision=backbone_precision,
+                       head_precision=head_precision).eval()
     seeded_fill(net, seed)
     return net.to(device)
 
@@ -116,11 +118,12 @@ def make_inputs(scenes, seed0, npts=80000):
 
 
 # --------------------------------------------------------------------------------------------- CPU (reference arm)
-def cpu_sample(state, n_dec_objects=2, threads=None):
+def cpu_sample(state, budget_s=30.0):
     """One bounded sample of the reference algorithm on the host cores: the full detection path on ONE 80k scene
-    (C oracle with OpenMP for the index kernels, PyTorch CPU for the MLPs) + the ONet decoder on `n_dec_objects`
-    objects x 32^3 points (exactly the per-object call of generator.py:131-141).  Seconds per scene are
-    extrapolated: t_detect + 256 * t_decode_per_object."""
+    (C oracle with OpenMP for the index kernels, PyTorch CPU for the MLPs) + the ONet decoder, one object x 32^3
+    points per call exactly like generator.py:131-141, on as many of the scene's 256 objects as fit in `budget_s`
+    seconds (all 256 when they fit: then nothing is extrapolated).
+    -> dict(per_scene_s, t_detect_s, t_decode_per_object_s, objects_measured, extrapolated, wall_s)"""
     from oracle import model_ref
     sd, pc, codes, grid = state["sd"], state["pc_cpu"], state["codes_cpu"], state["grid_cpu"]
     t0 = time.perf_counter()
@@ -130,12 +133,25 @@ def cpu_sample(state, n_dec_objects=2, threads=None):
         model_ref.proposal(vx, vf, sd, prefix="detection.detection", recip=False)
     t1 = time.perf_counter()
     dsd = {k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}
+    n = 0
     with torch.no_grad():
-        for o in range(n_dec_objects):
-            model_ref.decoder(grid.unsqueeze(0), torch.zeros(1, 32), codes[o:o + 1], dsd)
+        while n < 256:
+            model_ref.decoder(grid.unsqueeze(0), torch.zeros(1, 32), codes[n:n + 1], dsd)
+            n += 1
+            if time.perf_counter() - t0 > budget_s and n < 256:
+                break
     t2 = time.perf_counter()
-    t_det, t_dec = t1 - t0, (t2 - t1) / n_dec_objects
-    return t_det + 256.0 * t_dec, t_det, t_dec
+    t_det, t_dec = t1 - t0, (t2 - t1) / n
+    return {"per_scene_s": t_det + 256.0 * t_dec, "t_detect_s": t_det, "t_decode_per_object_s": t_dec,
+            "objects_measured": n, "extrapolated": n < 256, "wall_s": t2 - t0}
+
+
+def cpu_sample_text(r):
+    return (f"detection path on 1 scene of 80k pts ({r['t_detect_s']:.2f}s: C oracle + OpenMP index kernels, torch CPU "
+            f"MLPs) + ONet decoder on {r['objects_measured']} of the scene's 256 objects x 32^3 pts "
+            f"({r['t_decode_per_object_s']:.3f}s/object, torch CPU fp32)"
+            + ("; remaining objects extrapolated at the measured per-object time" if r["extrapolated"] else
+               "; the whole scene was measured, nothing extrapolated"))
 
 
 def run_reference(args, rank, world):
@@ -148,23 +164,24 @@ def run_reference(args, rank, world):
     sd = {k: v for k, v in net.state_dict().items()}
     pc, codes = make_inputs(1, 0)
     state = {"sd": sd, "pc_cpu": pc, "codes_cpu": codes, "grid_cpu": model_ref.make_3d_grid(32, 1.1)}
-    for _ in range(args.warmup):
-        cpu_sample(state, 1)
-    times = []
-    for _ in range(args.steps):
-        times.append(cpu_sample(state, 1))
-    per_scene = float(np.mean([t[0] for t in times]))
+    # every step is a bounded sample; the whole run must end within a few minutes
+    budget = max(4.0, min(40.0, 240.0 / (args.steps + 1)))
+    cpu_sample(state, budget_s=min(budget, 8.0))  # one short warm-up sample (thread pools, allocator)
+    res = [cpu_sample(state, budget_s=budget) for _ in range(args.steps)]
+    per_scene = float(np.mean([r["per_scene_s"] for r in res]))
     cores = oracle.num_threads()
-    sample = ("per step: detection path on 1 scene of 80k pts (C oracle + OpenMP, torch CPU MLPs) + ONet decoder on 1 "
-              "object x 32^3 pts (torch CPU fp32), extrapolated to 256 objects/scene; "
-              f"t_detect={np.mean([t[1] for t in times]):.2f}s t_decode/object={np.mean([t[2] for t in times]):.3f}s")
+    best = max(res, key=lambda r: r["objects_measured"])
     val = 1.0 / per_scene
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "scenes/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_scene * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "full hot path: 80k-pt scene -> backbone+vote+256 proposals -> ONet 256x32^3",
-                       "scenes_per_step": 1},
-            "cpu_baseline": {"value": val, "unit": "scenes/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "scenes_per_gpu_per_step": 1, "points": 80000, "proposals": 256, "grid": 32},
+            "cpu_baseline": {"value": val, "unit": "scenes/s", "cores": cores, "kind": "port",
+                             "sample": "per step: " + cpu_sample_text(best),
+                             "objects_measured": int(np.min([r["objects_measured"] for r in res])),
+                             "extrapolated": bool(any(r["extrapolated"] for r in res)),
+                             "measured_wall_ms_per_step": float(np.mean([r["wall_s"] for r in res])) * 1e3,
+                             "warmup_done": 1},
             "e2e": {"value": val, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -178,7 +195,8 @@ def run_gpu(args, rank, world, local):
     phys = int(visible.split(",")[local]) if visible and visible.split(",")[local].isdigit() else local
     bind_to_gpu_numa_node(phys)
     S = args.scenes
-    net = build_model(dev, backbone_precision=args.backbone_precision)
+    net = build_model(dev, backbone_precision=args.backbone_precision, head_precision=args.head_precision,
+                      decoder_precision=args.decoder_precision)
     sets = [make_inputs(S, 1000 * rank + 100 * i) for i in range(2)]  # two rotating input sets
     dev_sets = [(pc.to(dev), codes.to(dev)) for pc, codes in sets]
     host_sets = [(pc.pin_memory(), codes.pin_memory()) for pc, codes in sets]
@@ -232,16 +250,16 @@ def run_gpu(args, rank, world, local):
 
     if rank != 0:
         return
-    # ---- per-kernel device times
+    # ---- per-kernel device times (CUDA events recorded around the launches inside the timed steps)
     dec = [(s.elapsed_time(e), w) for n, s, e, w in timers if n == "onet_decode"]
-    qg = [(s.elapsed_time(e), w) for n, s, e, w in timers if n == "query_and_group"]
     dec_ms = float(np.mean([t for t, _ in dec]))
     dec_tflops = float(np.mean([w for _, w in dec])) / (dec_ms * 1e-3) / 1e12
-    qg_gbs = sum(w for _, w in qg) / (sum(t for t, _ in qg) * 1e-3) / 1e9
-    satc = [(s.elapsed_time(e), w) for n, s, e, w in timers if n == "sa_mlp_tc"]
-    satc_tflops = (sum(w for _, w in satc) / (sum(t for t, _ in satc) * 1e-3) / 1e12) if satc else None
+    chain = [(s.elapsed_time(e), w) for n, s, e, w in timers if n == "mlp_chain_tc"]
+    chain_tflops = (sum(w for _, w in chain) / (sum(t for t, _ in chain) * 1e-3) / 1e12) if chain else None
+    fps = [s.elapsed_time(e) for n, s, e, w in timers if n == "fps"]
     value = world * S * args.steps / (ms_max * 1e-3)
     e2e = world * S * args.steps / t_e2e
+    qg = ballquery_group_bench(net, dev_sets[0][0], hbm)
 
     # ---- CPU baseline (bounded sample, rank 0, N = 1 only)
     cpu = None
@@ -255,35 +273,38 @@ def run_gpu(args, rank, world, local):
         torch.set_num_threads(os.cpu_count() or 1)
         sd = {k: v.cpu() for k, v in net.state_dict().items()}
         state = {"sd": sd, "pc_cpu": sets[0][0], "codes_cpu": sets[0][1], "grid_cpu": model_ref.make_3d_grid(32, 1.1)}
-        per_scene, t_det, t_dec = cpu_sample(state, 2)
-        cpu = {"value": 1.0 / per_scene, "unit": "scenes/s", "cores": oracle.num_threads(), "kind": "port",
-               "sample": f"1 scene detection path ({t_det:.2f}s: C oracle+OpenMP index kernels, torch CPU MLPs) + ONet "
-                         f"decoder on 2 objects x 32^3 ({t_dec:.3f}s/object, torch CPU fp32), extrapolated to 256 objects"}
+        r = cpu_sample(state, budget_s=25.0)
+        cpu = {"value": 1.0 / r["per_scene_s"], "unit": "scenes/s", "cores": oracle.num_threads(), "kind": "port",
+               "sample": cpu_sample_text(r), "objects_measured": r["objects_measured"],
+               "extrapolated": r["extrapolated"], "measured_wall_s": r["wall_s"]}
 
-    traffic = None
+    traffic = traffic_src = None
     tp = os.path.join(ROOT, "profiles", "onet_decode_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+    dec_mode = args.decoder_precision
     line = {
         "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "full hot path: 80k-pt scene -> backbone(4 SA+2 FP, %s)+vote+256 proposals (vote-agg MLP bf16 "
-                               "tcgen05) -> ONet decoder 256 x 32^3 (bf16 tcgen05, fp32 accumulate)" % args.backbone_precision,
+        "vs_baseline": None, "dtype": {"fp16": "fp16", "bf16": "bf16", "fp16x3": "fp16x3"}[dec_mode], "data": "synthetic",
+        "config": {"workload": WORKLOAD + " [decoder: %s tcgen05, fp32 accumulate/residual; backbone MLPs: %s; "
+                               "vote/proposal MLPs: %s]" % (dec_mode, args.backbone_precision, args.head_precision),
                    "scenes_per_gpu_per_step": S, "points": 80000, "proposals": 256, "grid": 32,
                    "parallelism": f"dp{world} (scenes sharded, no collective)",
                    "l2": "per-step working set (logits %d MB + clouds) exceeds the 126 MB L2; inputs rotate over 2 sets"
                          % (S * 256 * 32768 * 4 // 2 ** 20)},
         "roofline": {"kernel": "onet_decode_kernel", "bound": "tensor", "achieved": dec_tflops, "peak": tc_sust,
-                     "unit": "TFLOP/s", "frac": dec_tflops / tc_sust, "traffic": traffic,
+                     "unit": "TFLOP/s", "frac": dec_tflops / tc_sust, "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})", "ms_per_launch": dec_ms,
-                     "flop_per_launch": float(np.mean([w for _, w in dec]))},
-        "ballquery_group": {"achieved": qg_gbs, "peak": hbm, "unit": "GB/s", "frac": qg_gbs / hbm,
-                            "launches_per_step": len(qg) // args.steps, "bound": "hbm",
-                            "ms_per_step": sum(t for t, _ in qg) / args.steps},
-        "sa_mlp_tc": {"achieved": satc_tflops, "unit": "TFLOP/s", "launches_per_step": len(satc) // args.steps,
-                      "ms_per_step": sum(t for t, _ in satc) / args.steps if satc else None,
-                      "layers": "vote-aggregation SA (config 3)" + (" + SA1-4" if args.backbone_precision == "bf16" else "")},
+                     "flop_per_launch": float(np.mean([w for _, w in dec])),
+                     "note": "algorithmic FLOP (1,312,768 per query point); fp16x3 issues 3 MMAs per algorithmic one"},
+        "ballquery_group": qg,
+        "mlp_chain_tc": {"achieved": chain_tflops, "unit": "TFLOP/s", "launches_per_step": len(chain) // args.steps,
+                         "ms_per_step": sum(t for t, _ in chain) / args.steps if chain else None,
+                         "layers": "SA1-4 (gather-fused), FP1-2, voting, vote-aggregation SA, proposal head",
+                         "note": "algorithmic FLOP; mode x3 issues 3 MMAs per algorithmic one"},
+        "fps": {"ms_per_step": sum(fps) / args.steps if fps else None, "launches_per_step": len(fps) // args.steps},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": t_e2e / args.steps * 1e3},
@@ -291,6 +312,49 @@ def run_gpu(args, rank, world, local):
         "clocks": clocks,
     }
     print(json.dumps(line))
+
+
+def ballquery_group_bench(net, pc, hbm_peak, iters=20):
+    """rfd_query_and_group (the drop-in QueryAndGroup operator) on the five layer shapes of THIS step's
+    scenes: algorithmic bytes (12N + 12M + 4CN + 4(3+C)MS per scene) / CUDA-event time of `iters`
+    back-to-back launches per layer, after warm-up.  The fused inference path never materialises the grouped tensor
+    (mlp_chain_tc gathers through the ball-query indices), so the operator is timed here on its own."""
+    from rfdnet_b200 import pointnet2_utils as pu
+    bb = net.detection.backbone
+    with torch.no_grad():
+        ep, _ = net.detection(pc)
+    xyz = pc[..., :3].contiguous()
+    feats = pc[..., 3:].transpose(1, 2).contiguous()
+    agg = net.detection.detection.vote_aggregation
+    shapes = [("SA1", xyz, ep["sa1_xyz"], feats, bb.sa1), ("SA2", ep["sa1_xyz"], ep["sa2_xyz"], ep["sa1_features"], bb.sa2),
+              ("SA3", ep["sa2_xyz"], ep["sa3_xyz"], ep["sa2_features"], bb.sa3),
+              ("SA4", ep["sa3_xyz"], ep["sa4_xyz"], ep["sa3_features"], bb.sa4),
+              ("vote-agg", ep["vote_xyz"], ep["aggregated_vote_xyz"], ep["vote_features"], agg)]
+    per, tot_b, tot_ms = {}, 0.0, 0.0
+    for name, src, q, f, mod in shapes:
+        src, q, f = src.contiguous(), q.contiguous(), f.contiguous()
+        B, N, _ = src.shape
+        M, C, Sn = q.shape[1], f.shape[1], mod.nsample
+        for _ in range(3):
+            pu.fused_query_and_group(src, q, f, mod.radius, Sn, True, True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            pu.fused_query_and_group(src, q, f, mod.radius, Sn, True, True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        nbytes = B * (12 * N + 12 * M + 4 * C * N + 4 * (3 + C) * M * Sn)
+        per[name] = {"us": ms * 1e3, "MB": nbytes / 1e6, "GB/s": nbytes / (ms * 1e-3) / 1e9,
+                     "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak}
+        tot_b += nbytes
+        tot_ms += ms
+    gbs = tot_b / (tot_ms * 1e-3) / 1e9
+    return {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "bound": "hbm",
+            "us_all_layers": tot_ms * 1e3, "per_layer": per,
+            "how": f"{iters} back-to-back launches per layer between CUDA events, incl. the grid build (SA1) and the "
+                   "feature transposition pass; outputs rotate through L2 (73 MB at SA2)"}
 
 
 def main():
@@ -301,8 +365,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=4, help="scenes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--backbone-precision", default="fp32", choices=["fp32", "bf16"],
-                    help="shared MLPs of SA1-4: fp32 CUDA cores (BASELINE config 2, default) or bf16 tcgen05")
+    ap.add_argument("--backbone-precision", default="x3", choices=["x3", "fp16", "bf16", "cuda"],
+                    help="MLPs of SA1-4 / FP1-2 (BASELINE config 2 is fp32): x3 = split-fp16 tcgen05, fp32-grade (default); "
+                         "fp16 / bf16 = single-MMA tcgen05; cuda = fp32 CUDA-core layer kernel")
+    ap.add_argument("--head-precision", default="x3", choices=["x3", "fp16", "bf16", "cuda"],
+                    help="voting MLP, vote-aggregation SA layer, proposal head (BASELINE config 3)")
+    ap.add_argument("--decoder-precision", default="fp16", choices=["fp16", "fp16x3", "bf16"],
+                    help="ONet decoder tcgen05 mode: fp16 (<= 1e-3, BASELINE config 4), fp16x3 (<= 1e-4), bf16 (legacy)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -28,6 +28,7 @@
  *   rfd_three_interpolate_grad   <- three_interpolate_grad    include/interpolate.h:9-10, src/interpolate.cpp:71-100
  *   rfd_query_and_group          <- QueryAndGroup.forward     ../pointnet2_utils.py:302-361 (ball_query + 2x group_points + sub + div + cat)
  *   rfd_pointwise_mlp_f32        <- Conv{1,2}d(1x1)+BatchNorm(eval)+ReLU(+max_pool2d)  ../pointnet2_modules.py:9-19,237-243
+ *   rfd_mlp_chain, rfd_sa_mlp_chain <- the same stacks per module on tensor cores (see below)
  *   rfd_three_nn_interpolate     <- PointnetFPModule.forward 3-NN + weights + interpolate  ../pointnet2_modules.py:381-389
  *   rfd_onet_*                   <- DecoderCBatchNorm.forward /root/reference/models/iscnet/modules/occ_decoder.py:110-122
  *                                   (+ layers.py:98-107 CResnetBlockConv1d, :226-242 CBatchNorm1d), eval mode
@@ -49,7 +50,7 @@ extern "C" {
 #define RFD_ERR_CUDA (-3)             /* a CUDA runtime call or launch failed; see rfd_last_error() */
 #define RFD_ERR_NO_DEVICE (-4)        /* no sm_100 device / wrong architecture */
 
-#define RFD_ABI_VERSION 2
+#define RFD_ABI_VERSION 3
 
 int rfd_abi_version(void);
 const char *rfd_status_string(int status);
@@ -65,6 +66,17 @@ int rfd_furthest_point_sampling(const float *xyz, int B, int N, int m, int *idx,
 /* same, additionally emitting the sampled coordinates new_xyz (B,m,3) f32 (NULL = skip): replaces the
  * transpose + gather_points + transpose of PointnetSAModuleVotes.forward (../pointnet2_modules.py:219-226). */
 int rfd_furthest_point_sampling_xyz(const float *xyz, int B, int N, int m, int *idx, float *new_xyz, void *stream);
+
+/* FPS of a cloud that is itself in FPS order (SA(k+1) samples SA(k)'s samples, pointnet2backbone.py:104-113) returns
+ * 0..m-1.  rfd_fps_prefix_check PROVES per scene whether rfd_furthest_point_sampling(xyz)[0..m) == (0,1,...,m-1), with
+ * the sampler's own arithmetic and tie-break, as one parallel sweep instead of m-1 serial rounds:
+ *   flag (B) i32 = 1 iff proved; own_ws: scratch, B*m floats.  m <= 3072 (larger: flag = 0).
+ * rfd_furthest_point_sampling_cond is the sampler with that flag (NULL = always sample): scenes whose flag is non-zero
+ * get idx = 0..m-1 (and new_xyz = xyz[0..m)) immediately, the others run the full sampler -- results are identical
+ * to rfd_furthest_point_sampling_xyz in both cases. */
+int rfd_fps_prefix_check(const float *xyz, int B, int N, int m, float *own_ws, int *flag, void *stream);
+int rfd_furthest_point_sampling_cond(const float *xyz, int B, int N, int m, const int *prefix_flag, int *idx,
+                                     float *new_xyz, void *stream);
 
 /* ---- (a2) gather: points (B,C,N), idx (B,M) -> out (B,C,M);  grad: grad_out (B,C,M) -> grad_points (B,C,N) */
 int rfd_gather_points(const float *points, const int *idx, int B, int C, int N, int M, float *out, void *stream);
@@ -85,7 +97,9 @@ int rfd_group_points_grad(const float *grad_out, const int *idx, int B, int C, i
  * xyz (B,N,3), new_xyz (B,M,3), features (B,C,N) or NULL (C=0)
  *   -> new_features (B, (use_xyz?3:0)+C, M, S) ; grouped_xyz (B,3,M,S) or NULL ; idx (B,M,S) or NULL.
  * grouped xyz = (xyz[idx] - new_xyz) and, when normalize_xyz, * (1.0f/radius) -- the CUDA reference
- * (torch `tensor /= python_float` lowers to a multiply by the f32 reciprocal).  nsample <= 128. */
+ * (torch `tensor /= python_float` lowers to a multiply by the f32 reciprocal).  nsample <= 1024.
+ * Uses a persistent per-(device, stream) workspace (uniform grid for N >= 8192, point-major feature copy) grown with
+ * cudaMalloc on first use: run once eagerly before capturing the call in a CUDA graph. */
 int rfd_query_and_group(const float *xyz, const float *new_xyz, const float *features, int B, int N, int M, int C,
                         float radius, int nsample, int use_xyz, int normalize_xyz, float *new_features,
                         float *grouped_xyz, int *idx, void *stream);
@@ -111,24 +125,40 @@ int rfd_pointwise_mlp_f32(const float *x, const float *W, const float *scale, co
                           const float *residual, int relu, int pool, int B, int Cin, int Cout, int L, float *y,
                           void *stream);
 
-/* ---- (a6) grouped shared-MLP + max over nsample on tcgen05 tensor cores (bf16 operands, fp32 accumulate; eval mode).
- * Replaces the three Conv2d(1x1)+BN2d+ReLU and the max_pool2d of PointnetSAModuleVotes.forward
- * (../pointnet2_modules.py:9-19,237-243) for one SA layer in one kernel.
- *   pack (once per checkpoint): W_l (C_l, C_{l-1}) f32 row-major, BN scale_l (C_l) folded into the bf16 weights
- *     -> packed (rfd_sa_mlp_tc_packed_bytes bytes, 0 = unsupported widths);
- *   run: x (B, Ct, M, S) f32 grouped tensor, shift (C1+C2+C3) f32 -> out (B, C3, M) f32 = max_s relu(...).
- * Supported: Ct <= 320; C1, C2 in {64,128}; C3 in {64,128,192,256}; S in {16,32,64,128}. */
-size_t rfd_sa_mlp_tc_packed_bytes(int Ct, int C1, int C2, int C3);
-int rfd_sa_mlp_tc_pack(const float *W1, const float *scale1, const float *W2, const float *scale2, const float *W3,
-                       const float *scale3, int Ct, int C1, int C2, int C3, void *packed, void *stream);
-int rfd_sa_mlp_tc(const float *x, int B, int Ct, int M, int S, const void *packed, const float *shift, int C1, int C2,
-                  int C3, float *out, void *stream);
-/* full set-abstraction fusion: same kernel, but the (B,3+C,M,S) grouped tensor is never
- * materialised -- the A tiles are gathered from xyz (B,N,3) / features (B,C,N) through idx (B,M,S) (rfd_ball_query),
- * centred on new_xyz (B,M,3) and scaled by 1/radius when normalize_xyz, exactly as rfd_query_and_group would. */
-int rfd_sa_gather_mlp_tc(const float *xyz, const float *new_xyz, const float *features, const int *idx, int B, int N,
-                         int M, int S, int C, float radius, int normalize_xyz, const void *packed, const float *shift,
-                         int C1, int C2, int C3, float *out, void *stream);
+/* ---- (a6/a9/a10/a11) every dense pointwise MLP of the detection pass on tcgen05 tensor cores (eval mode).
+ * One kernel per module replaces the Conv(1x1)+BatchNorm+ReLU stacks (and the max_pool2d of an SA layer) of
+ * PointnetSAModuleVotes (../pointnet2_modules.py:9-19,237-243), PointnetFPModule (:395-405), VotingModule
+ * (vote_module.py:34-61) and the ProposalModule head (proposal_module.py:85-124).
+ *   mode: RFD_MLP_MODE_BF16 / _F16 (one MMA per K step) or _F16X3 (split fp16, a_hi.w_hi + a_lo.w_hi + a_hi.w_lo:
+ *         fp32-grade results, BASELINE config 2's 1e-4) -- fp32 accumulation and fp32 BatchNorm affine in every mode.
+ *   layers: 1..3, widths C1, C2, C3 (0 = layer absent); hidden widths <= 256, last width <= 512; every layer
+ *         computes y = scale * (W . x) + shift (the folded BatchNorm / conv bias), hidden layers apply ReLU, the last
+ *         one iff relu_last.
+ *   pack (once per checkpoint): W_l (C_l, C_{l-1}) f32 row-major; W1 is (C1, xyz + K0): with xyz = 3 its first three
+ *         input columns are the relative-xyz channels of an SA layer, which the kernel applies in fp32 from
+ *         (xyz[idx] - new_xyz) * (1/radius) instead of feeding them to the tensor cores.
+ *         -> packed (rfd_mlp_chain_packed_bytes bytes; 0 = unsupported widths).
+ *   rfd_mlp_chain: dense rows.  x (B, K0, L) channel-major -> out_cm (B, C, L/pool) and/or out_pm (B, L/pool, C)
+ *         (either may be NULL); pool = 1, or 16/32/64/128 = max over runs of `pool` consecutive rows (the grouped
+ *         (B,3+C,M,S) tensor viewed as L = M*S; pool > 32 needs relu_last).
+ *   rfd_sa_mlp_chain: full set-abstraction fusion: rows are gathered through idx (B,M,S)
+ *         (rfd_ball_query) from xyz (B,N,3) and POINT-MAJOR features feat_pm (B,N,C) (rfd_transpose_features, or the
+ *         out_pm of the previous layer), centred on new_xyz (B,M,3) exactly as rfd_query_and_group would -- the grouped
+ *         tensor is never materialised -- then MLP + max over S.  S in {16,32,64,128}. */
+#define RFD_MLP_MODE_BF16 1
+#define RFD_MLP_MODE_F16 2
+#define RFD_MLP_MODE_F16X3 3
+size_t rfd_mlp_chain_packed_bytes(int mode, int K0, int xyz, int C1, int C2, int C3);
+int rfd_mlp_chain_pack(int mode, int K0, int xyz, const float *W1, const float *scale1, const float *shift1, int C1,
+                       const float *W2, const float *scale2, const float *shift2, int C2, const float *W3,
+                       const float *scale3, const float *shift3, int C3, int relu_last, void *packed, void *stream);
+int rfd_mlp_chain(int mode, const float *x, int B, int K0, int L, const void *packed, int C1, int C2, int C3,
+                  int relu_last, int pool, float *out_cm, float *out_pm, void *stream);
+int rfd_sa_mlp_chain(int mode, const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx, int B, int N,
+                     int M, int S, int C, float radius, int normalize_xyz, const void *packed, int C1, int C2, int C3,
+                     float *out_cm, float *out_pm, void *stream);
+/* features (B,C,N) channel-major -> point-major (B,N,Cp), Cp >= C a multiple of 4, padding zero-filled */
+int rfd_transpose_features(const float *features, int B, int C, int N, int Cp, float *out, void *stream);
 
 /* ---- (a13) occupancy query lattice: out (R^3,3) f32 = box_size * linspace(-0.5,0.5,R) on each axis, z fastest */
 int rfd_make_3d_grid(int R, float box_size, float *out, void *stream);

@@ -34,7 +34,62 @@ def _run(cmd):
         raise RuntimeError("reference build step failed")
 
 
+REF_PY = "/root/reference/external/pointnet2_ops_lib/pointnet2_ops"
+PY_OUT = os.path.join(OUT, "py", "external", "pointnet2_ops_lib", "pointnet2_ops")
+
+
+def stage_py():
+    """Stage the reference's UNMODIFIED pointnet2_utils.py / pointnet2_modules.py under the git-ignored oracle/_ref/py/
+    (same package path as in the reference tree) so that the GPU box -- which has no /root/reference -- can execute the
+    reference's own Python over `rfdnet_b200.dropin.install()` and over the reference CUDA kernels (tests/test_gpu_dropin.py).
+    The files are build artefacts like _ref_ext.so: never committed."""
+    if not os.path.isdir(REF_PY):
+        return None
+    import shutil
+    os.makedirs(PY_OUT, exist_ok=True)
+    for f in ("pointnet2_utils.py", "pointnet2_modules.py"):
+        shutil.copyfile(os.path.join(REF_PY, f), os.path.join(PY_OUT, f))
+    return PY_OUT
+
+
+def load_py(ext, tag):
+    """Import the staged reference modules with `pointnet2_ops._ext` bound to `ext` (ours or _ref_ext).
+    -> (pointnet2_utils, pointnet2_modules) as fresh module objects named *_<tag>; None if not staged."""
+    import importlib.util
+    import types
+    if not os.path.exists(os.path.join(PY_OUT, "pointnet2_modules.py")):
+        return None
+    saved = {k: sys.modules.get(k) for k in ("pointnet2_ops", "pointnet2_ops._ext", "external", "external.pointnet2_ops_lib",
+                                              "external.pointnet2_ops_lib.pointnet2_ops")}
+    try:
+        pkg = types.ModuleType("pointnet2_ops")
+        pkg.__path__ = []
+        pkg._ext = ext
+        sys.modules["pointnet2_ops"], sys.modules["pointnet2_ops._ext"] = pkg, ext
+        spec = importlib.util.spec_from_file_location("ref_pointnet2_utils_" + tag, os.path.join(PY_OUT, "pointnet2_utils.py"))
+        utils = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(utils)       # executes `import pointnet2_ops._ext as _ext` (pointnet2_utils.py:8)
+        assert utils._ext is ext
+        for name in ("external", "external.pointnet2_ops_lib", "external.pointnet2_ops_lib.pointnet2_ops"):
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+        sys.modules["external.pointnet2_ops_lib.pointnet2_ops"].pointnet2_utils = utils
+        spec = importlib.util.spec_from_file_location("ref_pointnet2_modules_" + tag, os.path.join(PY_OUT, "pointnet2_modules.py"))
+        mods = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mods)        # `from external.pointnet2_ops_lib.pointnet2_ops import pointnet2_utils` (:6)
+        assert mods.pointnet2_utils is utils
+        return utils, mods
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
 def build(force=False):
+    stage_py()
     so = os.path.join(OUT, MODNAME + ".so")
     if os.path.exists(so) and not force:
         return so

@@ -19,6 +19,8 @@ SIGNATURES = {
     "rfd_launch_count": [],
     "rfd_furthest_point_sampling": [_vp, _i, _i, _i, _vp, _vp],
     "rfd_furthest_point_sampling_xyz": [_vp, _i, _i, _i, _vp, _vp, _vp],
+    "rfd_fps_prefix_check": [_vp, _i, _i, _i, _vp, _vp, _vp],
+    "rfd_furthest_point_sampling_cond": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp],
     "rfd_gather_points": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "rfd_gather_points_grad": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "rfd_ball_query": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],
@@ -32,10 +34,11 @@ SIGNATURES = {
     "rfd_pointwise_mlp_f32": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "rfd_make_3d_grid": [_i, _f, _vp, _vp],
     "rfd_occupancy_bits": [_vp, _i, _i, _f, _vp, _vp, _vp],
-    "rfd_sa_mlp_tc_packed_bytes": [_i, _i, _i, _i],
-    "rfd_sa_mlp_tc_pack": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
-    "rfd_sa_mlp_tc": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
-    "rfd_sa_gather_mlp_tc": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "rfd_mlp_chain_packed_bytes": [_i, _i, _i, _i, _i, _i],
+    "rfd_mlp_chain_pack": [_i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp],
+    "rfd_mlp_chain": [_i, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "rfd_sa_mlp_chain": [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "rfd_transpose_features": [_vp, _i, _i, _i, _i, _vp, _vp],
     "rfd_onet_packed_bytes": [_i],
     "rfd_onet_pack_weights": [_vp, _i, _vp, _vp],
     "rfd_onet_aff_floats": [],
@@ -48,7 +51,7 @@ SIGNATURES = {
     "rfd_umma_selftest_ts": [_vp, _vp, _vp, _vp],
 }
 _RESTYPES = {"rfd_status_string": ctypes.c_char_p, "rfd_last_error": ctypes.c_char_p,
-             "rfd_launch_count": _ll, "rfd_onet_packed_bytes": _sz, "rfd_onet_aff_floats": _sz, "rfd_sa_mlp_tc_packed_bytes": _sz}
+             "rfd_launch_count": _ll, "rfd_onet_packed_bytes": _sz, "rfd_onet_aff_floats": _sz, "rfd_mlp_chain_packed_bytes": _sz}
 
 _lib = None
 

@@ -115,7 +115,7 @@ __device__ __forceinline__ FpsRec fps_pick(const FpsRec *recs, int n, int lane) 
 template <int PPT, int FPS_THREADS>
 __global__ void __launch_bounds__(FPS_THREADS, 1)
 fps_kernel(const float *__restrict__ xyz_all, int N, int m, int bs_log2, int Q, int CS, int *__restrict__ idx_all,
-           float *__restrict__ new_xyz_all) {
+           float *__restrict__ new_xyz_all, const int *__restrict__ prefix_flag) {
   extern __shared__ float4 s_pts[];  // [PPT][FPS_THREADS] this CTA's points (winner looks its xyz up here)
   constexpr int FPS_WARPS = FPS_THREADS / 32;
   __shared__ FpsRec s_warp[2][FPS_WARPS];
@@ -129,6 +129,19 @@ fps_kernel(const float *__restrict__ xyz_all, int N, int m, int bs_log2, int Q, 
   int *__restrict__ idx_out = idx_all + (size_t)scene * m;
   const int T = CS * FPS_THREADS;
   const int g = (int)rank * FPS_THREADS + tid;
+
+  // rfd_fps_prefix_check proved that sampling this scene returns 0, 1, ..., m-1 (the input is itself in FPS order):
+  // emit the identity and skip the m-1 serial rounds.  Uniform over the scene's cluster, before any cluster traffic.
+  if (prefix_flag && __ldg(prefix_flag + scene) != 0) {
+    for (int j = g; j < m; j += T) {
+      idx_out[j] = j;
+      if (new_xyz_all) {
+        float *o = new_xyz_all + ((size_t)scene * m + j) * 3;
+        o[0] = __ldg(xyz + (size_t)j * 3); o[1] = __ldg(xyz + (size_t)j * 3 + 1); o[2] = __ldg(xyz + (size_t)j * 3 + 2);
+      }
+    }
+    return;
+  }
 
   if (CS > 1) {
     if (tid == 0) {
@@ -241,7 +254,7 @@ fps_kernel(const float *__restrict__ xyz_all, int N, int m, int bs_log2, int Q, 
 
 template <int PPT, int FPS_THREADS>
 static int launch_fps(const float *xyz, int B, int N, int m, int bs_log2, int Q, int CS, int *idx, float *new_xyz,
-                      cudaStream_t stream, bool probe_only, int *max_clusters) {
+                      const int *prefix_flag, cudaStream_t stream, bool probe_only, int *max_clusters) {
   auto kern = fps_kernel<PPT, FPS_THREADS>;
   const size_t smem = (size_t)PPT * FPS_THREADS * sizeof(float4);
   RFD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fps attr smem");
@@ -266,15 +279,15 @@ static int launch_fps(const float *xyz, int B, int N, int m, int bs_log2, int Q,
     *max_clusters = n;
     return RFD_OK;
   }
-  RFD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, bs_log2, Q, CS, idx, new_xyz), "fps launch");
+  RFD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, bs_log2, Q, CS, idx, new_xyz, prefix_flag), "fps launch");
   RFD_CHECK_LAUNCH("fps_kernel");
   return RFD_OK;
 }
 
 static int dispatch_fps(int threads, int ppt, const float *xyz, int B, int N, int m, int bs_log2, int Q, int CS,
-                        int *idx, float *new_xyz, cudaStream_t stream, bool probe, int *maxc) {
+                        int *idx, float *new_xyz, const int *prefix_flag, cudaStream_t stream, bool probe, int *maxc) {
 #define RFD_FPS_CASE(P, T) \
-  if (ppt <= P) return launch_fps<P, T>(xyz, B, N, m, bs_log2, Q, CS, idx, new_xyz, stream, probe, maxc);
+  if (ppt <= P) return launch_fps<P, T>(xyz, B, N, m, bs_log2, Q, CS, idx, new_xyz, prefix_flag, stream, probe, maxc);
   if (threads == 1024) {
     RFD_FPS_CASE(1, 1024) RFD_FPS_CASE(2, 1024) RFD_FPS_CASE(3, 1024) RFD_FPS_CASE(4, 1024) RFD_FPS_CASE(5, 1024)
     RFD_FPS_CASE(6, 1024) RFD_FPS_CASE(8, 1024)
@@ -285,6 +298,82 @@ static int dispatch_fps(int threads, int ppt, const float *xyz, int B, int N, in
   RFD_FPS_CASE(24, 512)
 #undef RFD_FPS_CASE
   return RFD_ERR_UNSUPPORTED_SIZE;
+}
+
+// ------------------------------------------------------------------------------------------------
+// "FPS of an FPS-ordered prefix is the identity" (pointnet2backbone.py:104-113): SA(k+1) samples the points SA(k)
+// sampled, in the order SA(k) sampled them, and -- barring ties -- gets back 0, 1, ..., m-1 after m-1 SERIAL rounds.
+// Instead of trusting that, it is PROVED per scene, in parallel, with the sampler's own arithmetic:
+//   FPS(xyz)[0..m) == (0, 1, ..., m-1)   <=>   for every round j in 1..m-1, point j is the arg-max of
+//       D_j(k) = min(1e10, min_{i<j} d(p_k, p_i))   over the non-skipped points k,
+//   i.e. for every k != j:  D_j(k) < D_j(j)  or  (D_j(k) == D_j(j) and rank(j) < rank(k))      (tie-break of the sampler).
+// own[j] = D_j(j) costs thread j a loop over i < j (pass 1); thread k then walks j = 1..m-1 keeping D_j(k) as a running
+// minimum and compares it with own[j] (pass 2): the same n*m distance evaluations as the sampler, but as one wide
+// parallel sweep (~10 us) instead of m-1 dependent rounds (0.45 us each).  Any violated comparison (ties resolved the
+// other way, NaNs, skipped points among the first m) clears the scene's flag and the full sampler runs for that scene.
+constexpr int PFX_THREADS = 128;
+constexpr int PFX_MAX_M = 3072;  // pass 2 keeps m float4 records in dynamic shared memory (48 KB without opt-in)
+
+__device__ __forceinline__ bool fps_skipped(float x, float y, float z) {
+  float mag = __fmul_rn(y, y);
+  mag = __fmaf_rn(x, x, mag);
+  mag = __fmaf_rn(z, z, mag);
+  return (double)mag <= 1e-3;
+}
+
+// pass 1: own[j] = D_j(j) for j in 1..m-1 (-inf if point j is skipped: it can never be sampled); flag[b] = 1
+__global__ void __launch_bounds__(PFX_THREADS)
+fps_prefix_own_kernel(const float *__restrict__ xyz_all, int N, int m, float *__restrict__ own_all, int *__restrict__ flag) {
+  const int b = blockIdx.y;
+  const float *__restrict__ xyz = xyz_all + (size_t)b * N * 3;
+  const int j = blockIdx.x * PFX_THREADS + threadIdx.x;
+  if (j == 0) flag[b] = 1;
+  if (j < 1 || j >= m) return;
+  const float x = __ldg(xyz + (size_t)j * 3), y = __ldg(xyz + (size_t)j * 3 + 1), z = __ldg(xyz + (size_t)j * 3 + 2);
+  float D = fps_skipped(x, y, z) ? -INFINITY : 1e10f;
+  for (int i = 0; i < j; ++i) {
+    const float d = sqdist_yxz(x - __ldg(xyz + (size_t)i * 3), y - __ldg(xyz + (size_t)i * 3 + 1), z - __ldg(xyz + (size_t)i * 3 + 2));
+    D = fminf(d, D);
+  }
+  own_all[(size_t)b * m + j] = D;
+}
+
+// pass 2: thread k checks D_j(k) against own[j] for every round j
+__global__ void __launch_bounds__(PFX_THREADS)
+fps_prefix_verify_kernel(const float *__restrict__ xyz_all, int N, int m, int bs_log2, int Q,
+                         const float *__restrict__ own_all, int *__restrict__ flag) {
+  extern __shared__ float4 s_rec[];  // [j] = (p_{j-1}.xyz, own[j]), j = 1..m-1
+  const int b = blockIdx.y;
+  const float *__restrict__ xyz = xyz_all + (size_t)b * N * 3;
+  const float *__restrict__ own = own_all + (size_t)b * m;
+  for (int j = 1 + threadIdx.x; j < m; j += PFX_THREADS)
+    s_rec[j] = make_float4(__ldg(xyz + (size_t)(j - 1) * 3), __ldg(xyz + (size_t)(j - 1) * 3 + 1),
+                           __ldg(xyz + (size_t)(j - 1) * 3 + 2), __ldg(own + j));
+  __syncthreads();
+  const int k = blockIdx.x * PFX_THREADS + threadIdx.x;
+  if (k >= N) return;
+  const float x = __ldg(xyz + (size_t)k * 3), y = __ldg(xyz + (size_t)k * 3 + 1), z = __ldg(xyz + (size_t)k * 3 + 2);
+  if (fps_skipped(x, y, z)) return;  // never a candidate
+  const uint32_t bs_mask = (1u << bs_log2) - 1u;
+  auto rank_of = [&](uint32_t p) {
+    const uint32_t slot = p & bs_mask;
+    const uint32_t rev = bs_log2 ? (__brev(slot) >> (32 - bs_log2)) : 0u;
+    return rev * (uint32_t)Q + (p >> bs_log2);
+  };
+  const uint32_t rk = rank_of((uint32_t)k);
+  float D = 1e10f;
+  bool ok = true;
+#pragma unroll 4
+  for (int j = 1; j < m; ++j) {
+    const float4 r = s_rec[j];
+    const float d = sqdist_yxz(x - r.x, y - r.y, z - r.z);
+    D = fminf(d, D);
+    if (j != k) {
+      const bool fine = (D < r.w) || (D == r.w && rank_of((uint32_t)j) < rk);
+      ok = ok && fine;
+    }
+  }
+  if (!ok) flag[b] = 0;
 }
 
 // reference cuda_utils.h:15-19 (evaluated with the same double arithmetic)
@@ -317,11 +406,16 @@ int fps_plan(int N, int B, int num_sms, int threads, int *cs_out, int *ppt_out) 
 }  // namespace rfd
 
 extern "C" int rfd_furthest_point_sampling(const float *xyz, int B, int N, int m, int *idx, void *stream) {
-  return rfd_furthest_point_sampling_xyz(xyz, B, N, m, idx, nullptr, stream);
+  return rfd_furthest_point_sampling_cond(xyz, B, N, m, nullptr, idx, nullptr, stream);
 }
 
 extern "C" int rfd_furthest_point_sampling_xyz(const float *xyz, int B, int N, int m, int *idx, float *new_xyz,
                                                void *stream) {
+  return rfd_furthest_point_sampling_cond(xyz, B, N, m, nullptr, idx, new_xyz, stream);
+}
+
+extern "C" int rfd_furthest_point_sampling_cond(const float *xyz, int B, int N, int m, const int *prefix_flag, int *idx,
+                                                float *new_xyz, void *stream) {
   using namespace rfd;
   if (B < 0 || N < 1 || m < 0 || (B > 0 && (!xyz || (m > 0 && !idx)))) return RFD_ERR_INVALID_ARGUMENT;
   if (B == 0 || m == 0) return RFD_OK;
@@ -358,7 +452,7 @@ extern "C" int rfd_furthest_point_sampling_xyz(const float *xyz, int B, int N, i
       int &slot = cache[threads == 1024][p][c];
       if (slot == 0) {
         int maxc = 0;
-        rc = dispatch_fps(threads, p, xyz, B, N, m, bs_log2, Q, c, idx, new_xyz, st, true, &maxc);
+        rc = dispatch_fps(threads, p, xyz, B, N, m, bs_log2, Q, c, idx, new_xyz, nullptr, st, true, &maxc);
         if (rc != RFD_OK) return rc;
         slot = maxc + 1;
       }
@@ -379,5 +473,28 @@ extern "C" int rfd_furthest_point_sampling_xyz(const float *xyz, int B, int N, i
   }
   if (getenv("RFD_FPS_DEBUG"))
     fprintf(stderr, "[rfd fps] B=%d N=%d m=%d threads=%d cluster=%d points/thread=%d\n", B, N, m, threads, cs, ppt);
-  return dispatch_fps(threads, ppt, xyz, B, N, m, bs_log2, Q, cs, idx, new_xyz, st, false, nullptr);
+  return dispatch_fps(threads, ppt, xyz, B, N, m, bs_log2, Q, cs, idx, new_xyz, prefix_flag, st, false, nullptr);
+}
+
+extern "C" int rfd_fps_prefix_check(const float *xyz, int B, int N, int m, float *own_ws, int *flag, void *stream) {
+  using namespace rfd;
+  if (B < 0 || N < 1 || m < 0 || (B > 0 && (!xyz || !flag || (m > 1 && !own_ws)))) return RFD_ERR_INVALID_ARGUMENT;
+  if (B == 0) return RFD_OK;
+  cudaStream_t st = as_stream(stream);
+  if (m > N || m > PFX_MAX_M || B > 65535) {  // m > N can never be the identity; larger m: not supported, run the full FPS
+    RFD_CHECK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * (size_t)B, st), "fps_prefix memset");
+    return RFD_OK;
+  }
+  const int bs = ref_opt_n_threads(N);
+  int bs_log2 = 0;
+  while ((1 << bs_log2) < bs) ++bs_log2;
+  const int Q = (N + bs - 1) / bs;
+  fps_prefix_own_kernel<<<dim3(h_ceil_div(m > 0 ? m : 1, PFX_THREADS), B), PFX_THREADS, 0, st>>>(xyz, N, m, own_ws, flag);
+  RFD_CHECK_LAUNCH("fps_prefix_own_kernel");
+  if (m > 1) {
+    fps_prefix_verify_kernel<<<dim3(h_ceil_div(N, PFX_THREADS), B), PFX_THREADS, (size_t)m * sizeof(float4), st>>>(
+        xyz, N, m, bs_log2, Q, own_ws, flag);
+    RFD_CHECK_LAUNCH("fps_prefix_verify_kernel");
+  }
+  return RFD_OK;
 }

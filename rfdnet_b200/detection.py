@@ -16,10 +16,9 @@ from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
 
 
 class Pointnet2Backbone(nn.Module):
-    def __init__(self, input_feature_dim=1, fps_side_stream=False):
+    def __init__(self, input_feature_dim=1):
         super().__init__()
         self.input_feature_dim = input_feature_dim
-        self.fps_side_stream = fps_side_stream
         self.sa1 = PointnetSAModuleVotes(npoint=2048, radius=0.2, nsample=64,
                                          mlp=[self.input_feature_dim, 64, 64, 128], use_xyz=True, normalize_xyz=True)
         self.sa2 = PointnetSAModuleVotes(npoint=1024, radius=0.4, nsample=32, mlp=[128, 128, 128, 256],
@@ -32,34 +31,17 @@ class Pointnet2Backbone(nn.Module):
         self.fp2 = PointnetFPModule(mlp=[256 + 256, 256, 256])
 
     def _forward_fused(self, xyz, features, end_points):
-        """Inference schedule.  The four FPS runs only depend on coordinates (SA(k+1) samples the points SA(k)
-        sampled), so the serial FPS chain of SA2-4 CAN run on a side stream under SA1's ball query, grouping and
-        shared MLP (`fps_side_stream=True`).  Measured on B200 this is no faster (the one-CTA-per-scene FPS kernels
-        then share SMs with the MLP grid and slow down), so the default is the plain sequence."""
+        """Inference schedule: every SA layer hands its features to the next one in point-major layout (the layout
+        the gather of the tensor-core chain kernel reads), next to the channel-major tensors the reference exposes."""
         i1, x1 = pointnet2_utils.fps_with_xyz(xyz.contiguous(), self.sa1.npoint)
-        if self.fps_side_stream:
-            main = torch.cuda.current_stream(xyz.device)
-            if getattr(self, "_side", None) is None or self._side.device != xyz.device:
-                self._side = torch.cuda.Stream(xyz.device)
-            side = self._side
-            side.wait_stream(main)
-            x1.record_stream(side)
-            with torch.cuda.stream(side):
-                i2, x2 = pointnet2_utils.fps_with_xyz(x1, self.sa2.npoint)
-                i3, x3 = pointnet2_utils.fps_with_xyz(x2, self.sa3.npoint)
-                i4, x4 = pointnet2_utils.fps_with_xyz(x3, self.sa4.npoint)
-            _, f1, _ = self.sa1(xyz, features, i1, x1)
-            main.wait_stream(side)
-            for t in (i2, x2, i3, x3, i4, x4):
-                t.record_stream(main)
-        else:
-            _, f1, _ = self.sa1(xyz, features, i1, x1)
-            i2, x2 = pointnet2_utils.fps_with_xyz(x1, self.sa2.npoint)
-            i3, x3 = pointnet2_utils.fps_with_xyz(x2, self.sa3.npoint)
-            i4, x4 = pointnet2_utils.fps_with_xyz(x3, self.sa4.npoint)
-        _, f2, _ = self.sa2(x1, f1, i2, x2)
-        _, f3, _ = self.sa3(x2, f2, i3, x3)
-        _, f4, _ = self.sa4(x3, f3, i4, x4)
+        _, f1, _, p1 = self.sa1._forward_fused(xyz, features, i1, x1, want_pm=True)
+        # SA2-4 sample an FPS-ordered cloud: the identity result is proved per scene instead of re-running the sampler
+        i2, x2 = pointnet2_utils.fps_with_xyz(x1, self.sa2.npoint, try_prefix=True)
+        i3, x3 = pointnet2_utils.fps_with_xyz(x2, self.sa3.npoint, try_prefix=True)
+        i4, x4 = pointnet2_utils.fps_with_xyz(x3, self.sa4.npoint, try_prefix=True)
+        _, f2, _, p2 = self.sa2._forward_fused(x1, f1, i2, x2, features_pm=p1, want_pm=True)
+        _, f3, _, p3 = self.sa3._forward_fused(x2, f2, i3, x3, features_pm=p2, want_pm=True)
+        _, f4, _, _ = self.sa4._forward_fused(x3, f3, i4, x4, features_pm=p3)
         f = self.fp1(x3, x4, f3, f4)
         f = self.fp2(x2, x3, f2, f)
         end_points.update(sa1_inds=i1, sa1_xyz=x1, sa1_features=f1, sa2_inds=i2, sa2_xyz=x2, sa2_features=f2,
@@ -106,6 +88,7 @@ class Pointnet2Backbone(nn.Module):
 
 class _HeadFoldCache:
     """folded (W, scale, shift) of conv1/bn1, conv2/bn2, conv3 -- recomputed only after the weights change"""
+    precision = 'x3'  # 'x3' | 'fp16' | 'bf16': one tcgen05 chain kernel for the three convs; 'cuda': fp32 layer kernel
 
     def _heads(self):
         if getattr(self, "_hf", None) is None:
@@ -113,16 +96,34 @@ class _HeadFoldCache:
                         _mlp.fold_conv_bn(self.conv3, None))
         return self._hf
 
-    def train(self, mode=True):
+    def _run_heads(self, x):
+        """conv1+bn1+relu -> conv2+bn2+relu -> conv3 on x (B,C,L) f32 contiguous"""
+        h1, h2, h3 = self._heads()
+        if self.precision != 'cuda':
+            tc = getattr(self, "_tc", None)
+            if tc is None or tc[0] != self.precision:
+                tc = self._tc = (self.precision, _mlp.ChainMlp([(*h1, True), (*h2, True), (*h3, False)], xyz=0,
+                                                               mode=self.precision))
+            if tc[1].ok:
+                return tc[1].dense(x)[0]
+        net = _mlp.pointwise_layer(x, *h1, relu=True)
+        net = _mlp.pointwise_layer(net, *h2, relu=True)
+        return _mlp.pointwise_layer(net, *h3, relu=False)
+
+    def _drop_heads(self):
         self._hf = None
+        self._tc = None
+
+    def train(self, mode=True):
+        self._drop_heads()
         return super().train(mode)
 
     def _load_from_state_dict(self, *a, **k):
-        self._hf = None
+        self._drop_heads()
         return super()._load_from_state_dict(*a, **k)
 
     def _apply(self, fn, *a, **k):
-        self._hf = None
+        self._drop_heads()
         return super()._apply(fn, *a, **k)
 
 
@@ -141,13 +142,10 @@ class VotingModule(_HeadFoldCache, nn.Module):
     def forward(self, seed_xyz, seed_features):
         batch_size, num_seed = seed_xyz.shape[0], seed_xyz.shape[1]
         num_vote = num_seed * self.vote_factor
-        fast = not self.training and not torch.is_grad_enabled() and seed_features.is_cuda
+        fast = (not self.training and not torch.is_grad_enabled() and seed_features.is_cuda
+                and seed_features.dtype == torch.float32 and self.conv1.weight.device == seed_features.device)
         if fast:
-            x = seed_features.contiguous()
-            h1, h2, h3 = self._heads()
-            net = _mlp.pointwise_layer(x, *h1, relu=True)
-            net = _mlp.pointwise_layer(net, *h2, relu=True)
-            net = _mlp.pointwise_layer(net, *h3, relu=False)
+            net = self._run_heads(seed_features.contiguous())
         else:
             net = F.relu(self.bn1(self.conv1(seed_features)))
             net = F.relu(self.bn2(self.conv2(net)))
@@ -210,12 +208,10 @@ class ProposalModule(_HeadFoldCache, nn.Module):
             raise ValueError('Unknown sampling strategy: %s' % self.sampling)
         end_points['aggregated_vote_xyz'] = xyz
         end_points['aggregated_vote_inds'] = sample_inds
-        fast = not self.training and not torch.is_grad_enabled() and features.is_cuda
+        fast = (not self.training and not torch.is_grad_enabled() and features.is_cuda
+                and features.dtype == torch.float32 and self.conv1.weight.device == features.device)
         if fast:
-            h1, h2, h3 = self._heads()
-            net = _mlp.pointwise_layer(features.contiguous(), *h1, relu=True)
-            net = _mlp.pointwise_layer(net, *h2, relu=True)
-            net = _mlp.pointwise_layer(net, *h3, relu=False)
+            net = self._run_heads(features.contiguous())
         else:
             net = F.relu(self.bn1(self.conv1(features)))
             net = F.relu(self.bn2(self.conv2(net)))

@@ -46,9 +46,10 @@ def fold_sequential(seq):
 def pointwise_layer(x, W, scale, shift, relu, pool=1, residual=None):
     """y = act(scale * (W . x) + shift) (+ residual), optional max over runs of `pool` positions.
     x (B,Cin,L) f32 contiguous CUDA -> (B,Cout,L//pool)."""
+    check_f32(x, "x")
     B, Cin, L = x.shape
     Cout = W.shape[0]
-    assert W.shape[1] == Cin, (W.shape, Cin)
+    assert W.shape[1] == Cin and W.device == x.device, (W.shape, Cin)
     y = torch.empty((B, Cout, L // pool), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().rfd_pointwise_mlp_f32(
@@ -66,51 +67,104 @@ def run_mlp(x, layers, pool_last=1):
     return x
 
 
-class PackedMlp3:
-    """bf16 tensor-core weights of a 3-layer shared MLP (rfd_sa_mlp_tc_pack); None if the widths are unsupported."""
+MODES = {'bf16': 1, 'fp16': 2, 'x3': 3}
 
-    def __init__(self, layers):
-        (W1, s1, t1, r1), (W2, s2, t2, r2), (W3, s3, t3, r3) = layers
-        assert r1 and r2 and r3
-        self.Ct, self.C1, self.C2, self.C3 = W1.shape[1], W1.shape[0], W2.shape[0], W3.shape[0]
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class ChainMlp:
+    """1-3 folded pointwise layers [(W, scale, shift, relu), ...] packed for the tcgen05 chain kernel
+    (csrc/mlp_chain_tc.cu).  mode: 'x3' (split-fp16, fp32-grade: BASELINE config 2's 1e-4), 'fp16', 'bf16'.
+    xyz = 3: the first three input columns of layer 0 are the relative-xyz channels of an SA layer, applied in fp32
+    by the epilogue (gather mode).  `ok` is False when the widths are outside what the kernel supports."""
+
+    def __init__(self, layers, xyz=0, mode='x3'):
+        n = len(layers)
+        assert 1 <= n <= 3 and all(l[3] for l in layers[:-1]), "intermediate layers must have a ReLU"
+        self.mode, self.xyz = MODES[mode], int(xyz)
+        self.relu_last = int(bool(layers[-1][3]))
+        self.K0 = layers[0][0].shape[1] - self.xyz
+        self.C = [l[0].shape[0] for l in layers] + [0] * (3 - n)
+        self.out_C = layers[-1][0].shape[0]
+        self.flop_per_row = 2.0 * sum(l[0].shape[0] * l[0].shape[1] for l in layers)
         lib = _lib.load()
-        nbytes = lib.rfd_sa_mlp_tc_packed_bytes(self.Ct, self.C1, self.C2, self.C3)
+        nbytes = lib.rfd_mlp_chain_packed_bytes(self.mode, self.K0, self.xyz, *self.C)
         self.ok = nbytes > 0
         if not self.ok:
             return
-        dev = W1.device
+        dev = layers[0][0].device
         self.packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        self.shift = torch.cat([t1, t2, t3]).contiguous()
+        args = []
+        for i in range(3):
+            if i < n:
+                W, s, t, _ = layers[i]
+                self._keep = getattr(self, "_keep", []) + [W.contiguous(), s.contiguous(), t.contiguous()]
+                args += [self._keep[-3].data_ptr(), self._keep[-2].data_ptr(), self._keep[-1].data_ptr(), self.C[i]]
+            else:
+                args += [0, 0, 0, 0]
         with torch.cuda.device(dev):
-            _lib.check(lib.rfd_sa_mlp_tc_pack(W1.data_ptr(), s1.data_ptr(), W2.data_ptr(), s2.data_ptr(), W3.data_ptr(),
-                                              s3.data_ptr(), self.Ct, self.C1, self.C2, self.C3, self.packed.data_ptr(),
-                                              torch.cuda.current_stream().cuda_stream), "sa_mlp_tc_pack")
+            _lib.check(lib.rfd_mlp_chain_pack(self.mode, self.K0, self.xyz, *args, self.relu_last,
+                                              self.packed.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                       "mlp_chain_pack")
+        self._keep = None  # the packed image owns copies of everything
 
-    def __call__(self, grouped):
-        """grouped (B, Ct, M, S) f32 -> (B, C3, M) f32."""
-        B, Ct, M, S = grouped.shape
-        assert Ct == self.Ct
-        out = torch.empty((B, self.C3, M), dtype=torch.float32, device=grouped.device)
-        flop = 2.0 * B * M * S * (self.Ct * self.C1 + self.C1 * self.C2 + self.C2 * self.C3)
-        with torch.cuda.device(grouped.device), _lib.timed("sa_mlp_tc", flop):
-            _lib.check(_lib.load().rfd_sa_mlp_tc(grouped.data_ptr(), B, Ct, M, S, self.packed.data_ptr(),
-                                                 self.shift.data_ptr(), self.C1, self.C2, self.C3, out.data_ptr(),
-                                                 torch.cuda.current_stream().cuda_stream), "sa_mlp_tc")
-        return out
+    def _outs(self, B, rows, dev, want_cm, want_pm):
+        cm = torch.empty((B, self.out_C, rows), dtype=torch.float32, device=dev) if want_cm else None
+        pm = torch.empty((B, rows, self.out_C), dtype=torch.float32, device=dev) if want_pm else None
+        return cm, pm
 
-    def fused(self, xyz, new_xyz, features, idx, radius, normalize_xyz):
-        """Full SA fusion: gather + centre/normalise + 3-layer MLP + max without materialising the grouped tensor.
-        xyz (B,N,3), new_xyz (B,M,3), features (B,C,N) or None, idx (B,M,S) i32 -> (B, C3, M)."""
+    def dense(self, x, pool=1, want_cm=True, want_pm=False):
+        """x (B, K0, L) f32 channel-major -> (out_cm (B, C, L/pool) | None, out_pm (B, L/pool, C) | None)."""
+        check_f32(x, "x")
+        B, K0, L = x.shape
+        assert K0 == self.K0 and self.xyz == 0, (K0, self.K0)
+        cm, pm = self._outs(B, L // pool, x.device, want_cm, want_pm)
+        with torch.cuda.device(x.device), _lib.timed("mlp_chain_tc", B * L * self.flop_per_row):
+            _lib.check(_lib.load().rfd_mlp_chain(self.mode, x.data_ptr(), B, K0, L, self.packed.data_ptr(), *self.C,
+                                                 self.relu_last, int(pool), _ptr(cm), _ptr(pm),
+                                                 torch.cuda.current_stream().cuda_stream), "mlp_chain")
+        return cm, pm
+
+    def gather(self, xyz, new_xyz, feat_pm, idx, radius, normalize_xyz, want_cm=True, want_pm=False):
+        """Full SA fusion: rows gathered through idx (B,M,S) from xyz (B,N,3) / point-major features (B,N,C),
+        centred on new_xyz, 3-layer MLP, max over S -> (out_cm (B,C3,M) | None, out_pm (B,M,C3) | None)."""
+        check_f32(xyz, "xyz"); check_f32(new_xyz, "new_xyz")
         B, N, _ = xyz.shape
         _, M, S = idx.shape
-        C = 0 if features is None else features.shape[1]
-        assert 3 + C == self.Ct
-        out = torch.empty((B, self.C3, M), dtype=torch.float32, device=xyz.device)
-        flop = 2.0 * B * M * S * (self.Ct * self.C1 + self.C1 * self.C2 + self.C2 * self.C3)
-        with torch.cuda.device(xyz.device), _lib.timed("sa_mlp_tc", flop):
-            _lib.check(_lib.load().rfd_sa_gather_mlp_tc(
-                xyz.data_ptr(), new_xyz.data_ptr(), 0 if features is None else features.data_ptr(), idx.data_ptr(),
-                B, N, M, S, C, float(radius), int(bool(normalize_xyz)), self.packed.data_ptr(), self.shift.data_ptr(),
-                self.C1, self.C2, self.C3, out.data_ptr(), torch.cuda.current_stream().cuda_stream),
-                "sa_gather_mlp_tc")
-        return out
+        C = 0 if feat_pm is None else feat_pm.shape[2]
+        if feat_pm is not None:
+            check_f32(feat_pm, "features")
+            assert feat_pm.shape[:2] == (B, N)
+        assert C == self.K0 and self.xyz == 3 and idx.dtype == torch.int32 and idx.is_contiguous()
+        cm, pm = self._outs(B, M, xyz.device, want_cm, want_pm)
+        with torch.cuda.device(xyz.device), _lib.timed("mlp_chain_tc", B * M * S * self.flop_per_row):
+            _lib.check(_lib.load().rfd_sa_mlp_chain(
+                self.mode, xyz.data_ptr(), new_xyz.data_ptr(), _ptr(feat_pm), idx.data_ptr(), B, N, M, S, C,
+                float(radius), int(bool(normalize_xyz)), self.packed.data_ptr(), *self.C, _ptr(cm), _ptr(pm),
+                torch.cuda.current_stream().cuda_stream), "sa_mlp_chain")
+        return cm, pm
+
+
+def check_f32(t, name):
+    """Same precondition errors as the reference's CHECK_CUDA / CHECK_CONTIGUOUS / CHECK_IS_FLOAT (utils.h:5-25): the
+    raw-pointer entry points must never reinterpret a half / double / CPU / strided tensor as dense fp32."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be a float tensor")
+
+
+def transpose_to_point_major(features):
+    """(B, C, N) channel-major -> (B, N, Cp) point-major, Cp = C rounded up to 4 (rfd_transpose_features)."""
+    check_f32(features, "features")
+    B, C, N = features.shape
+    Cp = (C + 3) & ~3
+    out = torch.empty((B, N, Cp), dtype=torch.float32, device=features.device)
+    with torch.cuda.device(features.device):
+        _lib.check(_lib.load().rfd_transpose_features(features.data_ptr(), B, C, N, Cp, out.data_ptr(),
+                                                      torch.cuda.current_stream().cuda_stream), "transpose_features")
+    return out

@@ -269,6 +269,13 @@ def make_3d_grid(resolution=32, box_size=1.1, device='cuda'):
     return out
 
 
+def make_3d_grid_cpu(bb_min, bb_max, shape):
+    """General lattice of external/common.py:157-176 (x slowest, z fastest), built with torch on the host: only the
+    16^3 `export_shape` preview of ONet.compute_loss uses it; the 32^3 inference lattice comes from rfd_make_3d_grid."""
+    axes = [torch.linspace(bb_min[i], bb_max[i], shape[i]) for i in range(3)]
+    return torch.stack(torch.meshgrid(*axes, indexing='ij'), dim=-1).reshape(-1, 3)
+
+
 def occupancy_bits(logits, threshold=0.0):
     """logits (B,T) f32 cuda -> (bits (B, ceil(T/32)) int32 [bit t%32 of word t/32 = logit >= threshold], counts (B) i32).
     threshold 0.0 = logit(0.5), the reference's surface level (generator.py:160)."""

@@ -14,14 +14,17 @@ from . import detection, onet
 
 class SceneHotPath(nn.Module):
     def __init__(self, input_feature_dim=1, num_proposal=256, z_dim=32, c_dim=512, resolution=32, box_size=1.1,
-                 precision='fp16', backbone_precision='fp32', head_precision='bf16'):
-        """precision: ONet decoder ('fp16' | 'fp16x3' | 'bf16' tcgen05 modes, 'fp32' CUDA cores).  backbone_precision: shared MLPs of SA1-4
-        (BASELINE config 2: fp32).  head_precision: shared MLP of the vote-aggregation SA layer (BASELINE config 3:
-        bf16 tensor-core path)."""
+                 precision='fp16', backbone_precision='x3', head_precision='x3'):
+        """precision: ONet decoder ('fp16' | 'fp16x3' | 'bf16' tcgen05 modes, 'fp32' CUDA cores).
+        backbone_precision: the MLPs of SA1-4 / FP1-2 (BASELINE config 2 is fp32: 'x3' = split-fp16 tensor cores with
+        fp32-grade results; 'fp16' / 'bf16' single-MMA tensor-core modes; 'cuda' = fp32 CUDA-core layer kernel).
+        head_precision: voting MLP, vote-aggregation SA layer and proposal head (BASELINE config 3), same choices."""
         super().__init__()
         self.detection = detection.DetectionHotPath(input_feature_dim, num_proposal)
-        for name in ("sa1", "sa2", "sa3", "sa4"):
+        for name in ("sa1", "sa2", "sa3", "sa4", "fp1", "fp2"):
             getattr(self.detection.backbone, name).precision = backbone_precision
+        self.detection.voting.precision = head_precision
+        self.detection.detection.precision = head_precision
         self.detection.detection.vote_aggregation.precision = head_precision
         self.decoder = onet.DecoderCBatchNorm(dim=3, z_dim=z_dim, c_dim=c_dim, precision=precision)
         self.num_proposal, self.z_dim, self.c_dim = num_proposal, z_dim, c_dim

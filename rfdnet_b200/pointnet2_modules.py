@@ -5,7 +5,7 @@ PointnetSAModuleVotes :149-260, PointnetFPModule :345-405).
 Same constructor arguments, forward signatures, return values and state_dict keys
 (`mlp_module.{0,3,6}.weight`, `mlp_module.{1,4,7}.*`, `mlp.*`), so reference checkpoints load.
 In eval mode without autograd the forward runs entirely on the sm_100a kernels
-(FPS -> fused ball-query+group -> folded-BN MLP + max); with autograd enabled (training,
+(FPS -> ball query -> gather + folded-BN MLP + max in one tcgen05 kernel); with autograd enabled (training,
 config 5) the reference's op sequence runs on the drop-in `_ext` kernels + torch autograd.
 """
 from typing import List
@@ -55,15 +55,19 @@ class _FoldCache:
 
 
 class PointnetSAModuleVotes(_FoldCache, nn.Module):
-    """pointnet2_modules.py:149-260 (pooling 'max' | 'avg' | 'rbf')."""
+    """pointnet2_modules.py:149-260 (pooling 'max' | 'avg' | 'rbf').
+
+    precision (inference path): 'x3' (default) / 'fp16' / 'bf16' run FPS -> ball query -> ONE tcgen05 kernel that
+    gathers, centres, applies the three folded Conv+BN+ReLU layers and max-pools (csrc/mlp_chain_tc.cu; 'x3' = split
+    fp16, fp32-grade: BASELINE config 2's 1e-4); 'cuda' materialises the grouped tensor (rfd_query_and_group) and runs
+    the fp32 CUDA-core layer kernel (the round-1 path, kept as the exact yardstick)."""
 
     def __init__(self, *, mlp: List[int], npoint: int = None, radius: float = None, nsample: int = None,
                  bn: bool = True, use_xyz: bool = True, pooling: str = 'max', sigma: float = None,
                  normalize_xyz: bool = False, sample_uniformly: bool = False, ret_unique_cnt: bool = False,
-                 precision: str = 'fp32'):
+                 precision: str = 'x3'):
         super().__init__()
-        self.precision = precision  # 'fp32' (exact CUDA-core path) | 'bf16' (tcgen05 shared-MLP, eval only)
-        self.fuse_gather = True     # bf16 only: gather inside the MLP kernel, the grouped tensor is never materialised
+        self.precision = precision
         self.npoint, self.radius, self.nsample = npoint, radius, nsample
         self.pooling = pooling
         self.use_xyz = use_xyz
@@ -87,17 +91,31 @@ class PointnetSAModuleVotes(_FoldCache, nn.Module):
     def _fast_ok(self, xyz, features):
         return (not self.training and not torch.is_grad_enabled() and self.npoint is not None
                 and self.pooling == 'max' and not self.sample_uniformly and xyz.is_cuda
-                and self.nsample in (4, 8, 16, 32, 64))
+                and xyz.dtype == torch.float32 and (features is None or (features.dtype == torch.float32
+                                                                         and features.device == xyz.device))
+                and self.mlp_module[0].weight.device == xyz.device
+                and self.nsample in (4, 8, 16, 32, 64, 128))
 
     def forward(self, xyz, features=None, inds=None, new_xyz=None):
         """`new_xyz` (B,npoint,3), optional and only honoured together with `inds` on the fused inference path: the
-        sampled coordinates when the caller already ran FPS (Pointnet2Backbone pre-samples SA2-4 on a side stream)."""
+        sampled coordinates when the caller already ran FPS."""
         if self._fast_ok(xyz, features):
-            return self._forward_fused(xyz, features, inds, new_xyz)
+            return self._forward_fused(xyz, features, inds, new_xyz)[:3]
         return self._forward_reference(xyz, features, inds)
 
+    def _chain(self, layers):
+        """tensor-core chain of this layer's shared MLP (None: precision 'cuda' or unsupported widths)"""
+        if self.precision == 'cuda' or not self.use_xyz or len(layers) > 3 or self.nsample not in (16, 32, 64, 128):
+            return None
+        tc = getattr(self, "_tc", None)
+        if tc is None or tc[0] != self.precision:
+            tc = self._tc = (self.precision, _mlp.ChainMlp(layers, xyz=3, mode=self.precision))
+        return tc[1] if tc[1].ok else None
+
     # -- inference: sm_100a kernels end to end
-    def _forward_fused(self, xyz, features, inds, new_xyz=None):
+    def _forward_fused(self, xyz, features, inds, new_xyz=None, features_pm=None, want_pm=False):
+        """-> (new_xyz, new_features (B,C,npoint), inds, new_features point-major (B,npoint,C) | None).
+        features_pm: the same features already in point-major layout (B,N,C) (the previous layer's second output)."""
         xyz = xyz.contiguous()
         B, N, _ = xyz.shape
         if inds is not None and new_xyz is not None:
@@ -108,26 +126,28 @@ class PointnetSAModuleVotes(_FoldCache, nn.Module):
             assert inds.shape[1] == self.npoint
             new_xyz = pointnet2_utils._ext.gather_points(xyz.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
         layers = self._folded(self.mlp_module)
-        if (self.precision == 'bf16' and self.fuse_gather and self.use_xyz and len(layers) == 3
-                and self.nsample in (16, 32, 64)):
-            if getattr(self, "_tc", None) is None:
-                self._tc = _mlp.PackedMlp3(layers)
-            if self._tc.ok:
-                idx = pointnet2_utils._ext.ball_query(new_xyz, xyz, self.radius, self.nsample)
-                feats = None if features is None else features.contiguous()
-                return new_xyz, self._tc.fused(xyz, new_xyz, feats, idx, self.radius, self.normalize_xyz), inds
+        chain = self._chain(layers)
+        if chain is not None:
+            idx = pointnet2_utils._ext.ball_query(new_xyz, xyz, self.radius, self.nsample)
+            if features is None:
+                fpm = None
+            elif features_pm is not None:
+                fpm = features_pm
+            elif features.shape[1] == 1:
+                fpm = features.contiguous().view(B, N, 1)  # one channel: channel-major == point-major
+            else:
+                fpm = _mlp.transpose_to_point_major(features.contiguous())
+                if fpm.shape[2] != features.shape[1]:
+                    fpm = fpm[:, :, :features.shape[1]].contiguous()
+            cm, pm = chain.gather(xyz, new_xyz, fpm, idx, self.radius, self.normalize_xyz, True, want_pm)
+            return new_xyz, cm, inds, pm
         grouped, _, _ = pointnet2_utils.fused_query_and_group(
             xyz, new_xyz, None if features is None else features.contiguous(), self.radius, self.nsample,
             self.use_xyz, self.normalize_xyz)
         Ct = grouped.shape[1]
-        if self.precision == 'bf16' and len(layers) == 3 and self.nsample in (16, 32, 64):
-            if getattr(self, "_tc", None) is None:
-                self._tc = _mlp.PackedMlp3(layers)
-            if self._tc.ok:
-                return new_xyz, self._tc(grouped), inds
         x = grouped.view(B, Ct, self.npoint * self.nsample)
         new_features = _mlp.run_mlp(x, layers, pool_last=self.nsample)
-        return new_xyz, new_features, inds
+        return new_xyz, new_features, inds, None
 
     # -- training / generic: the reference's sequence (:219-260) on the drop-in ops
     def _forward_reference(self, xyz, features, inds):
@@ -159,13 +179,17 @@ class PointnetSAModuleVotes(_FoldCache, nn.Module):
 class PointnetFPModule(_FoldCache, nn.Module):
     """pointnet2_modules.py:345-405."""
 
-    def __init__(self, mlp, bn=True):
+    def __init__(self, mlp, bn=True, precision='x3'):
         super().__init__()
         self.mlp = build_shared_mlp(list(mlp), bn=bn)
+        self.precision = precision  # 'x3' | 'fp16' | 'bf16' tcgen05 chain, 'cuda' fp32 CUDA-core layers
         self._fold = None
 
     def forward(self, unknown, known, unknow_feats, known_feats):
-        fast = (not self.training and not torch.is_grad_enabled() and known is not None and unknown.is_cuda)
+        fast = (not self.training and not torch.is_grad_enabled() and known is not None and unknown.is_cuda
+                and unknown.dtype == known.dtype == known_feats.dtype == torch.float32
+                and (unknow_feats is None or unknow_feats.dtype == torch.float32)
+                and self.mlp[0].weight.device == unknown.device)
         if fast:
             unknown, known = unknown.contiguous(), known.contiguous()
             known_feats = known_feats.contiguous()
@@ -180,7 +204,14 @@ class PointnetFPModule(_FoldCache, nn.Module):
                     x.data_ptr(), torch.cuda.current_stream().cuda_stream), "three_nn_interpolate")
             if C1:
                 x[:, C2:, :] = unknow_feats
-            return _mlp.run_mlp(x, self._folded(self.mlp))
+            layers = self._folded(self.mlp)
+            if self.precision != 'cuda' and len(layers) <= 3:
+                tc = getattr(self, "_tc", None)
+                if tc is None or tc[0] != self.precision:
+                    tc = self._tc = (self.precision, _mlp.ChainMlp(layers, xyz=0, mode=self.precision))
+                if tc[1].ok:
+                    return tc[1].dense(x)[0]
+            return _mlp.run_mlp(x, layers)
         if known is not None:
             dist, idx = pointnet2_utils.three_nn(unknown, known)
             dist_recip = 1.0 / (dist + 1e-8)

@@ -116,22 +116,50 @@ class BallQuery(Function):
 ball_query = BallQuery.apply
 
 
-def fps_with_xyz(xyz, npoint):
-    """FPS that also returns the sampled coordinates (B,npoint,3) straight from the kernel (inference path)."""
+def fps_with_xyz(xyz, npoint, try_prefix=False):
+    """FPS that also returns the sampled coordinates (B,npoint,3) straight from the kernel (inference path).
+
+    try_prefix: the caller expects `xyz` to be in FPS order already (SA(k+1) samples the points SA(k) sampled,
+    pointnet2backbone.py:104-113), in which case the answer is 0..npoint-1.  That is PROVED per scene by
+    rfd_fps_prefix_check (a parallel sweep with the sampler's own arithmetic and tie-break, ~10 us) and the serial sampler
+    is skipped for the scenes where it holds; the others run it.  The result is identical either way."""
+    _mlp_check_f32(xyz, "points")
     B, N, _ = xyz.shape
+    npoint = int(npoint)
     idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
     new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device)
+    lib = _lib.load()
     with torch.cuda.device(xyz.device), _lib.timed("fps", float(B) * (12.0 * N + 4.0 * npoint)):
-        _lib.check(_lib.load().rfd_furthest_point_sampling_xyz(xyz.data_ptr(), B, N, int(npoint), idx.data_ptr(),
-                                                                new_xyz.data_ptr(),
-                                                                torch.cuda.current_stream().cuda_stream), "fps")
+        st = torch.cuda.current_stream().cuda_stream
+        flag = 0
+        if try_prefix and npoint <= N:
+            ws = torch.empty((B, max(npoint, 1)), dtype=torch.float32, device=xyz.device)
+            flag_t = torch.empty((B,), dtype=torch.int32, device=xyz.device)
+            _lib.check(lib.rfd_fps_prefix_check(xyz.data_ptr(), B, N, npoint, ws.data_ptr(), flag_t.data_ptr(), st),
+                       "fps_prefix_check")
+            flag = flag_t.data_ptr()
+        _lib.check(lib.rfd_furthest_point_sampling_cond(xyz.data_ptr(), B, N, npoint, flag, idx.data_ptr(),
+                                                        new_xyz.data_ptr(), st), "fps")
     return idx, new_xyz
+
+
+def _mlp_check_f32(t, name):
+    from .mlp import check_f32
+    check_f32(t, name)
 
 
 def fused_query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz=True, normalize_xyz=False,
                           ret_grouped_xyz=False, ret_idx=False):
     """One kernel for QueryAndGroup.forward (pointnet2_utils.py:319-344): ball query + both gathers +
     centring + radius normalisation + concatenation.  Inference path (no autograd graph)."""
+    _mlp_check_f32(xyz, "xyz")
+    _mlp_check_f32(new_xyz, "new_xyz")
+    if features is not None:
+        _mlp_check_f32(features, "features")
+        if features.device != xyz.device:
+            raise RuntimeError("features must be a CUDA tensor")
+    if new_xyz.device != xyz.device:
+        raise RuntimeError("new_xyz must be a CUDA tensor")
     B, N, _ = xyz.shape
     M = new_xyz.shape[1]
     C = 0 if features is None else features.shape[1]
@@ -171,7 +199,7 @@ class QueryAndGroup(nn.Module):
             xyz.requires_grad or new_xyz.requires_grad or (features is not None and features.requires_grad))
         if features is None:
             assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
-        if not needs_grad and not self.sample_uniformly and self.nsample <= 128:
+        if not needs_grad and not self.sample_uniformly and self.nsample <= 1024 and xyz.is_cuda:
             new_features, grouped_xyz, _ = fused_query_and_group(
                 xyz.contiguous(), new_xyz.contiguous(), None if features is None else features.contiguous(),
                 self.radius, self.nsample, self.use_xyz, self.normalize_xyz, ret_grouped_xyz=self.ret_grouped_xyz)

@@ -30,7 +30,7 @@ int main(void) {
   EXPECT(rfd_three_nn(NULL, NULL, 1, 8, 8, NULL, NULL, NULL) == RFD_ERR_INVALID_ARGUMENT);
   EXPECT(rfd_pointwise_mlp_f32(NULL, NULL, NULL, NULL, NULL, 1, 1, 1, 4, 4, 16, NULL, NULL) == RFD_ERR_INVALID_ARGUMENT);
   EXPECT(rfd_onet_decode(NULL, 0, 1, 128, NULL, NULL, 1, NULL, NULL, 0.f, NULL, NULL) == RFD_ERR_INVALID_ARGUMENT);
-  EXPECT(rfd_sa_mlp_tc(NULL, 1, 4, 8, 16, NULL, NULL, 64, 64, 128, NULL, NULL) == RFD_ERR_INVALID_ARGUMENT);
+  EXPECT(rfd_mlp_chain(RFD_MLP_MODE_F16X3, NULL, 1, 4, 128, NULL, 64, 64, 128, 1, 16, NULL, NULL, NULL) == RFD_ERR_INVALID_ARGUMENT);
   /* empty work is a no-op success */
   EXPECT(rfd_furthest_point_sampling(NULL, 0, 16, 4, NULL, NULL) == RFD_OK);
   EXPECT(rfd_ball_query(NULL, NULL, 0, 8, 8, 0.1f, 4, NULL, NULL) == RFD_OK);
@@ -43,8 +43,10 @@ int main(void) {
   EXPECT(rfd_onet_packed_bytes(0) == 0 && rfd_onet_packed_bytes(4) == 0);
   EXPECT(rfd_onet_decode((const float *)1, 0, 1, 128, NULL, NULL, 7, NULL, NULL, 0.f, NULL, NULL) == RFD_ERR_INVALID_ARGUMENT);
   EXPECT(rfd_onet_decode_set_cluster(3) == RFD_ERR_INVALID_ARGUMENT);
-  EXPECT(rfd_sa_mlp_tc_packed_bytes(259, 128, 128, 256) == (size_t)5 * 128 * 128 + 2 * 128 * 128 + 2 * 256 * 128);
-  EXPECT(rfd_sa_mlp_tc_packed_bytes(400, 128, 128, 256) == 0);
+  /* weight stages (4 + 2 + 2 K panels) + xyz table (256 x 16 B) + scale / shift tables (2 x 4 KB) */
+  EXPECT(rfd_mlp_chain_packed_bytes(RFD_MLP_MODE_F16, 256, 3, 128, 128, 256) == (size_t)4 * 128 * 128 + 2 * 128 * 128 + 2 * 256 * 128 + 4096 + 8192);
+  EXPECT(rfd_mlp_chain_packed_bytes(RFD_MLP_MODE_F16X3, 256, 3, 128, 128, 256) == (size_t)2 * (4 * 128 * 128 + 2 * 128 * 128 + 2 * 256 * 128) + 4096 + 8192);
+  EXPECT(rfd_mlp_chain_packed_bytes(RFD_MLP_MODE_F16, 256, 0, 300, 128, 256) == 0); /* hidden width > 256 */
   {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {

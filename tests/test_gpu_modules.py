@@ -91,11 +91,16 @@ def test_detection_80k_batch_shapes_and_determinism():
     assert torch.isfinite(ep["center"]).all()
 
 
+CHAIN_TOL = {"x3": 1e-4, "fp16": 3e-3, "bf16": 2e-2}   # x max(1, output scale); x3 is the BASELINE config-2 bound
+
+
+@pytest.mark.parametrize("mode", ["x3", "fp16", "bf16"])
 @pytest.mark.parametrize("Ct,C1,C2,C3,M,S", [(4, 64, 64, 128, 2048, 64), (131, 128, 128, 256, 1024, 32),
-                                             (259, 128, 128, 256, 512, 16), (259, 128, 128, 128, 256, 16),
-                                             (259, 128, 128, 128, 100, 16), (20, 64, 128, 192, 37, 32)])
-def test_sa_shared_mlp_tensor_core_vs_fp32(Ct, C1, C2, C3, M, S):
-    """tcgen05 grouped MLP + max (bf16 operands, fp32 accumulate) against the exact fp32 CUDA-core path."""
+                                             (259, 128, 128, 256, 512, 16), (259, 128, 128, 128, 100, 16),
+                                             (20, 64, 128, 192, 37, 32), (70, 32, 48, 100, 9, 128)])
+def test_chain_mlp_pooled_vs_fp32(Ct, C1, C2, C3, M, S, mode):
+    """tcgen05 chain kernel on a materialised grouped tensor (dense rows + max over S) against the exact fp32
+    CUDA-core path and against the reference's own module sequence in torch fp32."""
     from rfdnet_b200 import mlp
     seq = pointnet2_modules.build_shared_mlp([Ct, C1, C2, C3]).eval()
     seeded_fill(seq, Ct + C3)
@@ -104,39 +109,78 @@ def test_sa_shared_mlp_tensor_core_vs_fp32(Ct, C1, C2, C3, M, S):
     x = torch.randn(2, Ct, M, S, generator=g).to(DEV)
     layers = mlp.fold_sequential(seq)
     ref = mlp.run_mlp(x.view(2, Ct, M * S), layers, pool_last=S)
-    tc = mlp.PackedMlp3(layers)
+    tc = mlp.ChainMlp(layers, xyz=0, mode=mode)
     assert tc.ok
-    out = tc(x)
-    assert out.shape == (2, C3, M)
+    out, out_pm = tc.dense(x.view(2, Ct, M * S), pool=S, want_cm=True, want_pm=True)
+    assert out.shape == (2, C3, M) and torch.equal(out_pm, out.transpose(1, 2))
     scale = float(ref.abs().max())
     err = float((out - ref).abs().max())
-    print(f"sa_mlp_tc Ct={Ct} S={S}: max|err| {err:.3e} scale {scale:.3f}")
-    assert err <= 2e-2 * max(1.0, scale)
-    # and against torch in fp32 (the reference's own module sequence, TF32 off)
-    tf32 = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
-    try:
-        with torch.no_grad():
-            t = torch.nn.functional.max_pool2d(seq(x), kernel_size=[1, S]).squeeze(-1)
-    finally:
-        torch.backends.cudnn.allow_tf32 = tf32
-    assert torch.allclose(ref, t, atol=1e-4, rtol=1e-4)
+    print(f"chain {mode} Ct={Ct} S={S}: max|err| {err:.3e} scale {scale:.3f}")
+    assert err <= CHAIN_TOL[mode] * max(1.0, scale)
+    if mode == "x3":
+        tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            with torch.no_grad():
+                t = torch.nn.functional.max_pool2d(seq(x), kernel_size=[1, S]).squeeze(-1)
+        finally:
+            torch.backends.cudnn.allow_tf32 = tf32
+        assert torch.allclose(out, t, atol=1e-4, rtol=1e-4)
 
 
-def test_detection_bf16_sa_path_close_to_fp32():
+@pytest.mark.parametrize("mode", ["x3", "fp16"])
+@pytest.mark.parametrize("spec,L,relu_last", [([512, 256, 256], 1024, True), ([256, 256, 256, 259], 1024, False),
+                                              ([128, 128, 128, 69], 256, False), ([80, 64, 32], 300, True),
+                                              ([40, 24], 77, False), ([300, 512], 130, True)])
+def test_chain_mlp_dense_heads_vs_fp32(spec, L, relu_last, mode):
+    """FP-module, voting and proposal-head shapes (no pooling; last layer up to 512 wide in two column blocks;
+    K0 = 512 streams through the resident A panels in two rounds)."""
+    from rfdnet_b200 import mlp
+    g = torch.Generator().manual_seed(L)
+    layers = []
+    for i in range(1, len(spec)):
+        W = (torch.randn(spec[i], spec[i - 1], generator=g) / spec[i - 1] ** 0.5).to(DEV)
+        s = (torch.rand(spec[i], generator=g) + 0.5).to(DEV)
+        t = (torch.randn(spec[i], generator=g) * 0.2).to(DEV)
+        layers.append((W, s, t, True if i < len(spec) - 1 else relu_last))
+    x = torch.randn(2, spec[0], L, generator=g).to(DEV)
+    ref = mlp.run_mlp(x, layers)
+    tc = mlp.ChainMlp(layers, xyz=0, mode=mode)
+    assert tc.ok
+    out, out_pm = tc.dense(x, want_cm=True, want_pm=True)
+    assert out.shape == ref.shape and torch.equal(out_pm, out.transpose(1, 2))
+    err, scale = float((out - ref).abs().max()), float(ref.abs().max())
+    print(f"chain dense {mode} {spec}: max|err| {err:.3e} scale {scale:.3f}")
+    assert err <= CHAIN_TOL[mode] * max(1.0, scale)
+
+
+def test_detection_16bit_paths_close_to_exact():
     net = detection.DetectionHotPath(1, 256).eval()
     seeded_fill(net, 5)
     net = net.to(DEV)
     pc = torch.from_numpy(scannet_like_batch(1, 80000, seed0=9)).to(DEV)
-    with torch.no_grad():
-        ep, _ = net(pc)
+
+    def set_precision(p):
         for m in net.modules():
-            if isinstance(m, pointnet2_modules.PointnetSAModuleVotes):
-                m.precision = 'bf16'
+            if hasattr(m, "precision"):
+                m.precision = p
+
+    with torch.no_grad():
+        set_precision('cuda')
+        ep_c, _ = net(pc)
+        set_precision('x3')
+        ep, _ = net(pc)
+        set_precision('fp16')
+        ep_h, _ = net(pc)
+        set_precision('bf16')
         ep_b, _ = net(pc)
-    assert torch.equal(ep["sa1_inds"], ep_b["sa1_inds"])
-    f, fb = ep["sa1_features"], ep_b["sa1_features"]
-    assert float((f - fb).abs().max()) <= 3e-2 * max(1.0, float(f.abs().max()))
+    assert torch.equal(ep["sa1_inds"], ep_b["sa1_inds"]) and torch.equal(ep["sa1_inds"], ep_c["sa1_inds"])
+    for k in ("sa1_features", "sa2_features", "sa4_features", "fp2_features"):
+        f = ep_c[k]
+        sc = max(1.0, float(f.abs().max()))
+        assert float((f - ep[k]).abs().max()) <= 1e-4 * sc, k        # tensor cores, fp32-grade
+        assert float((f - ep_h[k]).abs().max()) <= 1e-2 * sc, k
+        assert float((f - ep_b[k]).abs().max()) <= 6e-2 * sc, k
 
 
 def test_stn_group_vs_reference_golden(golden):
@@ -164,21 +208,24 @@ def test_stn_group_vs_reference_golden(golden):
 
 
 @pytest.mark.parametrize("N,npoint,radius,S,C,mlp", [(4096, 512, 0.3, 32, 5, [5, 64, 64, 128]), (2048, 1024, 0.4, 32, 128, [128, 128, 128, 256]),
-                                                     (1024, 256, 0.3, 16, 256, [256, 128, 128, 128]), (20000, 2048, 0.2, 64, 1, [1, 64, 64, 128])])
-def test_full_sa_fusion_equals_materialised_path(N, npoint, radius, S, C, mlp):
-    """gather + centre/normalise + 3-layer tcgen05 MLP + max WITHOUT materialising the grouped tensor
-    must be bit-identical to the same tensor-core kernel fed with the materialised (B,3+C,M,S) tensor."""
+                                                     (1024, 256, 0.3, 16, 256, [256, 128, 128, 128]), (20000, 2048, 0.2, 64, 1, [1, 64, 64, 128]),
+                                                     (3000, 100, 0.5, 128, 0, [0, 32, 64])])
+def test_full_sa_fusion_vs_materialised_fp32_path(N, npoint, radius, S, C, mlp):
+    """FPS -> ball query -> ONE kernel (gather + centre/normalise + tcgen05 MLP + max) WITHOUT
+    materialising the grouped tensor, against the materialised fp32 CUDA-core path: same indices, features to 1e-4."""
     sa = pointnet2_modules.PointnetSAModuleVotes(npoint=npoint, radius=radius, nsample=S, mlp=list(mlp), use_xyz=True,
-                                                 normalize_xyz=True, precision='bf16').eval()
+                                                 normalize_xyz=True, precision='cuda').eval()
     seeded_fill(sa, N + S)
     sa = sa.to(DEV)
     xyz = torch.from_numpy(scannet_like_batch(2, N, seed0=N)[..., :3].copy()).to(DEV)
     g = torch.Generator().manual_seed(C)
-    feats = torch.randn(2, C, N, generator=g).to(DEV)
+    feats = torch.randn(2, C, N, generator=g).to(DEV) if C else None
     with torch.no_grad():
-        sa.fuse_gather = False
         x1, f1, i1 = sa(xyz, feats)
-        sa.fuse_gather = True
-        x2, f2, i2 = sa(xyz, feats)
+        sa.precision = 'x3'
+        x2, f2, i2, p2 = sa._forward_fused(xyz, feats, None, want_pm=True)
     assert torch.equal(i1, i2) and torch.equal(x1, x2)
-    assert torch.equal(f1, f2)
+    assert torch.equal(p2, f2.transpose(1, 2))
+    err, scale = float((f1 - f2).abs().max()), float(f1.abs().max())
+    print(f"fused SA N={N} S={S} C={C}: max|err| {err:.3e} scale {scale:.3f}")
+    assert err <= 1e-4 * max(1.0, scale)

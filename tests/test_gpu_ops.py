@@ -132,7 +132,11 @@ def test_three_nn_and_interpolate(n, m):
 
 @pytest.mark.parametrize("N,M,C,r,S,norm", [(4096, 512, 0, 0.2, 32, True), (4096, 512, 64, 0.2, 32, True),
                                             (2048, 1024, 128, 0.4, 32, True), (1024, 300, 7, 0.3, 16, False),
-                                            (512, 256, 256, 1.2, 16, True), (333, 13, 5, 0.25, 64, True)])
+                                            (512, 256, 256, 1.2, 16, True), (333, 13, 5, 0.25, 64, True),
+                                            (6000, 200, 20, 0.2, 48, True),      # two staged chunks, S not a power of 2
+                                            (5000, 33, 130, 0.5, 1024, False),   # STN_Group-sized nsample, C % 4 != 0
+                                            (2049, 100, 9, 0.3, 8, True),        # scene 1 not 16-byte aligned: no bulk copy
+                                            (1024, 1024, 256, 0.3, 16, True), (700, 5, 33, 0.4, 3, True)])
 def test_fused_query_and_group_bit_exact(N, M, C, r, S, norm):
     cloud = uniform_cloud(2, N, seed=N + C)
     q = cloud[:, :M].copy()
@@ -224,7 +228,7 @@ def test_ball_query_grid_path_bit_exact(N, M, r, S):
     got = _ext.ball_query(cu(q), cu(cloud), r, S).cpu().numpy()
     assert np.array_equal(got, oracle.ball_query(q, cloud, r, S))
     if S <= 128:
-        feats = rng.normal(size=(2, 6, N)).astype(np.float32)
+        feats = rng.normal(size=(2, 6 if S != 32 else 70, N)).astype(np.float32)
         out, gxyz, idx = pointnet2_utils.fused_query_and_group(cu(cloud), cu(q), cu(feats), r, S, True, True,
                                                                ret_grouped_xyz=True, ret_idx=True)
         rf, rg, ri = model_ref.query_and_group(torch.from_numpy(cloud), torch.from_numpy(q), torch.from_numpy(feats),
@@ -240,6 +244,39 @@ def test_fps_fused_new_xyz_output():
         idx, new_xyz = pointnet2_utils.fps_with_xyz(x, m)
         assert torch.equal(idx, _ext.furthest_point_sampling(x, m))
         assert torch.equal(new_xyz, torch.gather(x, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)))
+
+
+def test_fps_prefix_check_and_conditional_sampler():
+    """rfd_fps_prefix_check proves FPS(x)[:m] == arange(m) for FPS-ordered inputs; whatever the verdict, the conditional
+    sampler returns exactly what the plain sampler returns (ties, duplicates, skipped points, unordered clouds)."""
+    scene = cu(scannet_like_batch(3, 30000, seed0=11)[..., :3].copy())
+    i1, x1 = pointnet2_utils.fps_with_xyz(scene, 2048)
+    lattice = cu(np.random.default_rng(8).integers(-3, 4, (3, 2048, 3)).astype(np.float32))       # massive ties
+    _, lat_fps = pointnet2_utils.fps_with_xyz(lattice, 2048)                                     # ... in FPS order
+    tricky = cu(np.concatenate([tricky_cloud(2048, seed=1)] * 3))
+    _, tricky_fps = pointnet2_utils.fps_with_xyz(tricky, 2048)
+    unordered = cu(uniform_cloud(3, 2048, seed=5))
+    mixed = torch.stack([x1[0], unordered[1], x1[2]]).contiguous()                               # per-scene verdicts
+    from rfdnet_b200 import _lib
+    lib = _lib.load()
+    for name, x, expect in (("fps-ordered", x1, [1, 1, 1]), ("unordered", unordered, [0, 0, 0]), ("mixed", mixed, [1, 0, 1]),
+                            ("lattice", lat_fps, None), ("tricky", tricky_fps, None)):
+        for m in (1024, 2048, 1, 700):
+            ref_i, ref_x = pointnet2_utils.fps_with_xyz(x, m)
+            got_i, got_x = pointnet2_utils.fps_with_xyz(x, m, try_prefix=True)
+            assert torch.equal(ref_i, got_i) and torch.equal(ref_x, got_x), (name, m)
+            ws = torch.empty((3, m), device=DEV)
+            flag = torch.full((3,), -1, dtype=torch.int32, device=DEV)
+            _lib.check(lib.rfd_fps_prefix_check(x.data_ptr(), 3, x.shape[1], m, ws.data_ptr(), flag.data_ptr(), 0), "check")
+            torch.cuda.synchronize()
+            ident = (ref_i.cpu() == torch.arange(m, dtype=torch.int32)).all(dim=1).int().tolist()
+            f = flag.cpu().tolist()
+            assert all(fi <= ii for fi, ii in zip(f, ident)), (name, m, f, ident)   # never claims an identity that is not one
+            if expect is not None and m > 1:
+                assert f == expect, (name, m, f)
+    # the backbone case: SA2 samples SA1's samples
+    i2, _ = pointnet2_utils.fps_with_xyz(x1, 1024, try_prefix=True)
+    assert torch.equal(i2.cpu(), torch.arange(1024, dtype=torch.int32).expand(3, -1))
 
 
 def test_empty_and_degenerate_inputs():
@@ -272,7 +309,11 @@ def test_error_paths_raise():
     with pytest.raises(RuntimeError, match="int tensor"):
         _ext.gather_points(torch.randn(1, 3, 32, device=DEV), torch.zeros((1, 4), dtype=torch.int64, device=DEV))
     with pytest.raises(RuntimeError, match="query_and_group"):
-        pointnet2_utils.fused_query_and_group(x, x[:, :4].contiguous(), None, 0.2, 256, True, True)  # nsample > 128
+        pointnet2_utils.fused_query_and_group(x, x[:, :4].contiguous(), None, 0.2, 2000, True, True)  # nsample > 1024
+    with pytest.raises(RuntimeError, match="float tensor"):
+        pointnet2_utils.fused_query_and_group(x.double(), x[:, :4].contiguous(), None, 0.2, 8, True, True)
+    with pytest.raises(RuntimeError, match="float tensor"):
+        pointnet2_utils.fps_with_xyz(x.half(), 4)
 
 
 def test_c_abi_device_round_trip(tmp_path):
