@@ -314,6 +314,38 @@ def run_gpu(args, rank, world, local):
     print(json.dumps(line))
 
 
+def graph_time(fn, iters, reps=3):
+    """Device time of one call of `fn` (ms): `iters` calls are captured into ONE CUDA graph (after an eager warm-up on the
+    capture stream, which also sizes the library's persistent workspace) and the replay is timed with CUDA events, so the
+    figure is the kernels' own time back to back, not Python / launch overhead."""
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            fn()
+    st.synchronize()
+    g = torch.cuda.CUDAGraph()
+    keep = []  # outputs stay alive: every captured call writes its own buffer (no L2-resident reuse of one block)
+    with torch.cuda.graph(g, stream=st):
+        for _ in range(iters):
+            keep.append(fn())
+    best = None
+    with torch.cuda.stream(st):
+        g.replay()
+        st.synchronize()
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            st.synchronize()
+            t = e0.elapsed_time(e1) / iters
+            best = t if best is None else min(best, t)
+    torch.cuda.current_stream().wait_stream(st)
+    del keep, g
+    return best
+
+
 def ballquery_group_bench(net, pc, hbm_peak, iters=20):
     """rfd_query_and_group (the drop-in QueryAndGroup operator) on the five layer shapes of THIS step's
     scenes: algorithmic bytes (12N + 12M + 4CN + 4(3+C)MS per scene) / CUDA-event time of `iters`
@@ -335,16 +367,7 @@ def ballquery_group_bench(net, pc, hbm_peak, iters=20):
         src, q, f = src.contiguous(), q.contiguous(), f.contiguous()
         B, N, _ = src.shape
         M, C, Sn = q.shape[1], f.shape[1], mod.nsample
-        for _ in range(3):
-            pu.fused_query_and_group(src, q, f, mod.radius, Sn, True, True)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            pu.fused_query_and_group(src, q, f, mod.radius, Sn, True, True)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
+        ms = graph_time(lambda: pu.fused_query_and_group(src, q, f, mod.radius, Sn, True, True), iters)
         nbytes = B * (12 * N + 12 * M + 4 * C * N + 4 * (3 + C) * M * Sn)
         per[name] = {"us": ms * 1e3, "MB": nbytes / 1e6, "GB/s": nbytes / (ms * 1e-3) / 1e9,
                      "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak}
@@ -353,8 +376,9 @@ def ballquery_group_bench(net, pc, hbm_peak, iters=20):
     gbs = tot_b / (tot_ms * 1e-3) / 1e9
     return {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "bound": "hbm",
             "us_all_layers": tot_ms * 1e3, "per_layer": per,
-            "how": f"{iters} back-to-back launches per layer between CUDA events, incl. the grid build (SA1) and the "
-                   "feature transposition pass; outputs rotate through L2 (73 MB at SA2)"}
+            "how": f"{iters} back-to-back calls per layer captured in one CUDA graph, replay timed with CUDA events (best "
+                   "of 3), incl. the grid build (SA1) and the feature transposition pass; every call writes a fresh "
+                   "output (the 20 outputs of a replay exceed the 126 MB L2)"}
 
 
 def main():

@@ -127,7 +127,9 @@ class ONet(nn.Module):
 
 
 class ResnetBlockFC(nn.Module):
-    """layers.py:9-48: x_s + fc_1(relu(fc_0(relu(x)))), linear shortcut when the widths differ, fc_1 zero-initialised."""
+    """layers.py:9-48: x_s + fc_1(relu(fc_0(relu(x)))), fc_1 zero-initialised.  The reference's activation is
+    nn.ReLU(inplace=True) (:30), so by the time its shortcut reads `x` (:41-44) the tensor already holds relu(x): the
+    residual branch is shortcut(relu(x)) (or relu(x) itself when the widths agree).  Reproduced here without the aliasing."""
 
     def __init__(self, size_in, size_out=None, size_h=None):
         super().__init__()
@@ -141,7 +143,8 @@ class ResnetBlockFC(nn.Module):
         nn.init.zeros_(self.fc_1.weight)
 
     def forward(self, x):
-        dx = self.fc_1(self.actvn(self.fc_0(self.actvn(x))))
+        x = self.actvn(x)
+        dx = self.fc_1(self.actvn(self.fc_0(x)))
         return (x if self.shortcut is None else self.shortcut(x)) + dx
 
 

@@ -36,7 +36,6 @@ namespace rfd {
 constexpr int BQ_WARPS = 8;  // warps per CTA (stand-alone ball query: queries per CTA)
 constexpr int BQ_THREADS = BQ_WARPS * 32;
 constexpr int QG_MAX_S = 1024;      // nsample limit of the fused kernel
-constexpr int QG_MAX_SLOTS = 2048;  // (query, sample) slots per CTA
 constexpr int QG_CHUNK = 4096;      // points staged in shared memory per pass (48 KB)
 constexpr int QG_TILE = 4096;       // per-warp transposition tile: 32 slots x 32 channels fp32
 
@@ -145,7 +144,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 //   2  exclusive scan of the histogram into shared memory (every CTA; CTA 0 also publishes it as start[])
 //   3  scatter: slot = start[cell] + (atomicSub(count[cell]) - 1); sorted[slot] = (x, y, z, id)
 // count[] is all-zero again on exit (every increment is undone by one decrement), so the workspace needs no memset
-// between calls.  Order inside a cell is arbitrary; the query ranks its hits by id.
+// between calls.  Order inside a cell is arbitrary; the query ranks its hits by id.  A thread handles its (<= GB_PPT)
+// points of a round as one batch -- all loads, then all atomics, then all stores, the cells kept in registers between
+// the phases -- so the kernel is bound by three cluster barriers and one L2 round trip per phase, not by per-point
+// latencies.
+constexpr int GB_PPT = 10;  // points per thread per round (8192 threads x 10 = 81920 points per round)
+
 __global__ void __cluster_dims__(GB_CS, 1, 1) __launch_bounds__(GB_THREADS, 1)
 grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridScene *__restrict__ gs,
                   int *__restrict__ count, int *__restrict__ start, float4 *__restrict__ sorted) {
@@ -159,17 +163,28 @@ grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridScene 
   count += (size_t)b * (GRID_NC + 1);
   start += (size_t)b * (GRID_NC + 1);
   sorted += (size_t)b * n;
-  const int stride = GB_CS * GB_THREADS;
+  constexpr int stride = GB_CS * GB_THREADS;
+  const int g0 = rank * GB_THREADS + tid;
+  const bool one_round = n <= stride * GB_PPT;
+  float px[GB_PPT], py[GB_PPT], pz[GB_PPT];
   // ---- 0: bounding box
   if (tid < 6) s_bbox[tid] = tid < 3 ? 0x7fffffff : (int)0x80000000;
   __syncthreads();
   {
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int k = rank * GB_THREADS + tid; k < n; k += stride) {
+    for (int r0 = 0; r0 < n; r0 += stride * GB_PPT) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float v = __ldg(p + (size_t)k * 3 + c);
-        if (v == v) { mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v); }
+      for (int i = 0; i < GB_PPT; ++i) {
+        const int k = r0 + g0 + i * stride;
+        float x = NAN, y = NAN, z = NAN;
+        if (k < n) { x = __ldg(p + (size_t)k * 3); y = __ldg(p + (size_t)k * 3 + 1); z = __ldg(p + (size_t)k * 3 + 2); }
+        px[i] = x; py[i] = y; pz[i] = z;
+      }
+#pragma unroll
+      for (int i = 0; i < GB_PPT; ++i) {
+        if (px[i] == px[i]) { mn[0] = fminf(mn[0], px[i]); mx[0] = fmaxf(mx[0], px[i]); }
+        if (py[i] == py[i]) { mn[1] = fminf(mn[1], py[i]); mx[1] = fmaxf(mx[1], py[i]); }
+        if (pz[i] == pz[i]) { mn[2] = fminf(mn[2], pz[i]); mx[2] = fmaxf(mx[2], pz[i]); }
       }
     }
 #pragma unroll
@@ -217,73 +232,112 @@ grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridScene 
     g.pad = 0;
   }
   if (rank == 0 && tid == 0) gs[b] = g;
-  // ---- 1: histogram
-  for (int k = rank * GB_THREADS + tid; k < n; k += stride)
-    atomicAdd(count + grid_cell(g, __ldg(p + (size_t)k * 3), __ldg(p + (size_t)k * 3 + 1), __ldg(p + (size_t)k * 3 + 2)), 1);
+  // ---- 1: histogram (the points of the last round are still in registers)
+  int cellv[GB_PPT];
+  for (int r0 = 0; r0 < n; r0 += stride * GB_PPT) {
+#pragma unroll
+    for (int i = 0; i < GB_PPT; ++i) {
+      const int k = r0 + g0 + i * stride;
+      if (!one_round && k < n) { px[i] = __ldg(p + (size_t)k * 3); py[i] = __ldg(p + (size_t)k * 3 + 1); pz[i] = __ldg(p + (size_t)k * 3 + 2); }
+      cellv[i] = k < n ? grid_cell(g, px[i], py[i], pz[i]) : -1;
+    }
+#pragma unroll
+    for (int i = 0; i < GB_PPT; ++i)
+      if (cellv[i] >= 0) atomicAdd(count + cellv[i], 1);
+  }
   umma::cluster_sync();
   // ---- 2: exclusive scan (warp w owns cells [1024 w, 1024 w + 1024))
   const int ncell = g.gx * g.gy * g.gz;
   {
-    int run = 0;
+    constexpr int PER = GRID_NC / 32 / 32;  // 32 coalesced rows of 32 cells per warp
     const int c0 = warp * (GRID_NC / 32);
-    if (c0 < ncell) {
-#pragma unroll 4
-      for (int it = 0; it < GRID_NC / 32 / 32; ++it) {
-        const int c = c0 + it * 32 + lane;
-        const int v = c < ncell ? __ldcg(count + c) : 0;
-        int inc = v;
+    int v[PER];
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, inc, off);
-          if (lane >= off) inc += t;
-        }
-        s_start[c] = run + inc - v;
-        run += __shfl_sync(0xffffffffu, inc, 31);
-      }
+    for (int it = 0; it < PER; ++it) {
+      const int c = c0 + it * 32 + lane;
+      v[it] = c < ncell ? __ldcg(count + c) : 0;
     }
-    if (lane == 0) s_wsum[warp] = run;
-    __syncthreads();
-    if (warp == 0) {
-      const int v = s_wsum[lane];
-      int inc = v;
+    int run = 0;
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      int inc = v[it];
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, inc, off);
         if (lane >= off) inc += t;
       }
-      s_wsum[lane] = inc - v;
+      v[it] = run + inc - v[it];
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) s_wsum[warp] = run;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = s_wsum[lane];
+      int inc = w;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+      }
+      s_wsum[lane] = inc - w;
     }
     __syncthreads();
     const int woff = s_wsum[warp];
-    if (c0 < ncell) {
-      for (int it = 0; it < GRID_NC / 32 / 32; ++it) {
-        const int c = c0 + it * 32 + lane;
-        const int v = s_start[c] + woff;
-        s_start[c] = v;
-        if (rank == 0 && c <= ncell) start[c] = c < ncell ? v : n;
-      }
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      const int c = c0 + it * 32 + lane;
+      const int val = v[it] + woff;
+      s_start[c] = val;
+      if (rank == 0 && c <= ncell) start[c] = c < ncell ? val : n;
     }
-    if (rank == 0 && tid == 0 && (ncell & 1023) == 0) start[ncell] = n;  // ncell on a warp-segment boundary
+    if (rank == 0 && tid == 0 && ncell == GRID_NC) start[GRID_NC] = n;
   }
+  __syncthreads();
   umma::cluster_sync();  // every CTA has read the histogram before anyone starts undoing it
-  // ---- 3: scatter
-  for (int k = rank * GB_THREADS + tid; k < n; k += stride) {
-    const float x = __ldg(p + (size_t)k * 3), y = __ldg(p + (size_t)k * 3 + 1), z = __ldg(p + (size_t)k * 3 + 2);
-    const int c = grid_cell(g, x, y, z);
-    const int pos = s_start[c] + atomicSub(count + c, 1) - 1;
-    sorted[pos] = make_float4(x, y, z, __int_as_float(k));
+  // ---- 3: scatter (coordinates are re-read: L2 hits, and they must not stay live across the scan)
+  for (int r0 = 0; r0 < n; r0 += stride * GB_PPT) {
+#pragma unroll
+    for (int i = 0; i < GB_PPT; ++i) {
+      const int k = r0 + g0 + i * stride;
+      float x = 0.f, y = 0.f, z = 0.f;
+      if (k < n) { x = __ldg(p + (size_t)k * 3); y = __ldg(p + (size_t)k * 3 + 1); z = __ldg(p + (size_t)k * 3 + 2); }
+      px[i] = x; py[i] = y; pz[i] = z;
+      if (!one_round) cellv[i] = k < n ? grid_cell(g, x, y, z) : -1;
+    }
+    int pos[GB_PPT];
+#pragma unroll
+    for (int i = 0; i < GB_PPT; ++i) pos[i] = cellv[i] >= 0 ? atomicSub(count + cellv[i], 1) - 1 : 0;
+#pragma unroll
+    for (int i = 0; i < GB_PPT; ++i)
+      if (cellv[i] >= 0)
+        sorted[s_start[cellv[i]] + pos[i]] = make_float4(px[i], py[i], pz[i], __int_as_float(r0 + g0 + i * stride));
   }
 }
 
-// Grid scan for one query by one warp: collects the hits of the 27 neighbouring cells in `hits` (shared, GRID_CAP
-// ints), ranks them by index and writes the first nsample into row[] in ascending index order.
-// Returns the hit count capped at nsample, or -1 if more than GRID_CAP hits were found (caller falls back).
+__device__ __forceinline__ float4 lds128(uint32_t a) { return umma::lds_f4(a); }
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ int4 lds_s128(uint32_t a) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+
+// Grid scan for one query by one warp: collects the hits of the 27 neighbouring cells in `hits` (shared-memory address,
+// GRID_CAP ints, 16-byte aligned), ranks them by index and writes the first nsample through `put(rank, id)` in ascending
+// index order.  Returns the hit count capped at nsample, or -1 if more than GRID_CAP hits were found (caller falls back).
+template <typename Put>
 __device__ __forceinline__ int ball_scan_grid(const float4 *__restrict__ sorted, const GridScene &g,
                                               const int *__restrict__ start, float qx, float qy, float qz,
-                                              float radius2, int nsample, int lane, int *hits, int *row, int &first) {
+                                              float radius2, int nsample, int lane, uint32_t hits, int &first, Put put) {
   const int cx = grid_coord(qx, g.ox, g.inv_cell, g.gx), cy = grid_coord(qy, g.oy, g.inv_cell, g.gy),
             cz = grid_coord(qz, g.oz, g.inv_cell, g.gz);
   int H = 0;
+  const unsigned lt = (1u << lane) - 1u;
   for (int ix = max(cx - 1, 0); ix <= min(cx + 1, g.gx - 1); ++ix)
     for (int iy = max(cy - 1, 0); iy <= min(cy + 1, g.gy - 1); ++iy) {
       // cells (ix, iy, z0..z1) are contiguous in the cell order => one contiguous run of the sorted array
@@ -302,20 +356,26 @@ __device__ __forceinline__ int ball_scan_grid(const float4 *__restrict__ sorted,
         }
         const unsigned mask = __ballot_sync(0xffffffffu, hit);
         if (mask) {
-          const int pos = H + __popc(mask & ((1u << lane) - 1u));
-          if (hit && pos < GRID_CAP) hits[pos] = k;
+          const int pos = H + __popc(mask & lt);
+          if (hit && pos < GRID_CAP) sts_s32(hits + 4u * pos, k);
           H += __popc(mask);
         }
       }
     }
   if (H > GRID_CAP) return -1;
+  // pad to a multiple of 4 with INT_MAX (never smaller than an id) so the ranking can read 16 bytes at a time
+  if (lane < 4 && H + lane < ((H + 3) & ~3)) sts_s32(hits + 4u * (H + lane), 0x7fffffff);
   __syncwarp();
   int mn = 0x7fffffff;
+  const int H4 = (H + 3) & ~3;
   for (int h = lane; h < H; h += 32) {
-    const int id = hits[h];
+    const int id = lds_s32(hits + 4u * h);
     int rank = 0;
-    for (int t = 0; t < H; ++t) rank += (hits[t] < id);
-    if (rank < nsample) row[rank] = id;
+    for (int t = 0; t < H4; t += 4) {  // every lane reads the same 16 bytes: one broadcast wavefront
+      const int4 o = lds_s128(hits + 4u * t);
+      rank += (o.x < id) + (o.y < id) + (o.z < id) + (o.w < id);
+    }
+    if (rank < nsample) put(rank, id);
     mn = min(mn, id);
   }
 #pragma unroll
@@ -329,7 +389,7 @@ __global__ void __launch_bounds__(BQ_THREADS)
 ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int n, int m, float radius,
                   int nsample, int *__restrict__ idx, const GridScene *__restrict__ gs, const int *__restrict__ gstart,
                   const float4 *__restrict__ gsorted) {
-  __shared__ int s_hits[BQ_WARPS][GRID_CAP];
+  __shared__ __align__(16) int s_hits[BQ_WARPS][GRID_CAP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int j = blockIdx.x * BQ_WARPS + warp;
@@ -342,7 +402,7 @@ ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
   int first, cnt = -1;
   if (gs)
     cnt = ball_scan_grid(gsorted + (size_t)b * n, gs[b], gstart + (size_t)b * (GRID_NC + 1), qx, qy, qz, radius2,
-                         nsample, lane, s_hits[warp], row, first);
+                         nsample, lane, umma::smem_u32(s_hits[warp]), first, [&](int pos, int k) { row[pos] = k; });
   if (cnt < 0)
     cnt = ball_scan(xyz, n, qx, qy, qz, radius2, nsample, lane, first, [&](int pos, int k) { row[pos] = k; });
   // reference :35-39: the first hit pre-fills every slot; no hit at all leaves the zero-initialised row
@@ -373,7 +433,8 @@ transpose_features_kernel(const float *__restrict__ f, int C, int N, int Cp, flo
 
 struct QgParams {
   const float *xyz, *new_xyz, *features, *feat_t;  // feat_t: point-major copy (B,N,Cp) or nullptr (direct gathers)
-  int n, m, C, Cp, nsample, qt;                    // qt: queries per CTA
+  int n, m, C, Cp, nsample;
+  int G;                                           // queries per warp task (G * nsample slots; G = 32/nsample for nsample < 32)
   float radius;
   int use_xyz, normalize_xyz, s_shift;             // s_shift: log2(nsample) or -1
   float *new_features, *grouped_xyz;
@@ -381,103 +442,148 @@ struct QgParams {
   const GridScene *gs;
   const int *gstart;
   const float4 *gsorted;
-  int cloud_floats;                                // shared-memory staging area (floats), 0 in grid mode
+  int cloud_pts;                                   // staged points per pass (multiple of 128), 0 in grid mode
 };
 
-// fused ball query + group.  grid = (ceil(M/qt), B), 256 threads, dynamic shared memory:
-//   [s_idx: qt*S ints][s_q: qt*3 floats][s_cnt, s_first: qt ints each][mbarrier 16 B]
-//   [cloud: cloud_floats floats | hits: 8 x GRID_CAP ints][tiles: 8 x 4 KB (only with feat_t)]
+constexpr int QG_MAX_G = 4;
+
+
+// One warp, one query, `np_pad` (multiple of 128) points staged in shared memory as xyz triples, NaN-padded: every lane
+// tests FOUR consecutive points per step (three 16-byte shared loads, conflict-free at the 48-byte lane stride), one
+// ballot decides whether the step has a hit at all.  Hits are written to row[] (shared, u32 address) in ascending index.
+__device__ __forceinline__ void ball_scan_staged(uint32_t cloud, int np_pad, int k0, float qx, float qy, float qz,
+                                                 float radius2, int nsample, int lane, uint32_t row, int &cnt, int &first) {
+  const unsigned lt = (1u << lane) - 1u;
+  for (int base = 0; base < np_pad && cnt < nsample; base += 128) {
+    const uint32_t a = cloud + (uint32_t)(base + 4 * lane) * 12u;
+    const float4 v0 = lds128(a), v1 = lds128(a + 16), v2 = lds128(a + 32);
+    const bool h0 = sqdist_yxz(qx - v0.x, qy - v0.y, qz - v0.z) < radius2;
+    const bool h1 = sqdist_yxz(qx - v0.w, qy - v1.x, qz - v1.y) < radius2;
+    const bool h2 = sqdist_yxz(qx - v1.z, qy - v1.w, qz - v2.x) < radius2;
+    const bool h3 = sqdist_yxz(qx - v2.y, qy - v2.z, qz - v2.w) < radius2;
+    const unsigned any = __ballot_sync(0xffffffffu, h0 | h1 | h2 | h3);
+    if (any) {
+      const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1),
+                     m2 = __ballot_sync(0xffffffffu, h2), m3 = __ballot_sync(0xffffffffu, h3);
+      if (cnt == 0) {
+        const int L = __ffs(any) - 1;
+        const int j0 = ((m0 >> L) & 1u) ? 0 : (((m1 >> L) & 1u) ? 1 : (((m2 >> L) & 1u) ? 2 : 3));
+        first = k0 + base + 4 * L + j0;
+      }
+      int pos = cnt + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
+      const int k = k0 + base + 4 * lane;
+      if (h0) { if (pos < nsample) sts_s32(row + 4u * pos, k); ++pos; }
+      if (h1) { if (pos < nsample) sts_s32(row + 4u * pos, k + 1); ++pos; }
+      if (h2) { if (pos < nsample) sts_s32(row + 4u * pos, k + 2); ++pos; }
+      if (h3) { if (pos < nsample) sts_s32(row + 4u * pos, k + 3); }
+      cnt += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+    }
+  }
+}
+
+// fused ball query + group.  grid = (ceil(ceil(M/G)/8), B), 256 threads.  Every WARP owns one task of G consecutive
+// queries (G * S output slots) end to end -- search, index write, xyz channels, feature tiles -- so after the cloud is
+// staged no block-wide barrier exists and a slow query (dense neighbourhood) delays nobody but its own warp.
+// dynamic shared memory: [mbarrier 16 B][cloud: cloud_pts * 12 B | hits: 8 x GRID_CAP ints][idx: 8 x G*S ints]
+//                        [tiles: 8 x 2 x 4 KB (only with feat_t)]
 __global__ void __launch_bounds__(BQ_THREADS)
 query_and_group_kernel(const QgParams P) {
   extern __shared__ __align__(128) uint8_t qg_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
-  const int S = P.nsample, n = P.n, m = P.m;
-  const int j0 = blockIdx.x * P.qt;
-  const int nq = min(P.qt, m - j0);  // queries of this CTA
+  const int S = P.nsample, n = P.n, m = P.m, G = P.G;
+  const int task = blockIdx.x * BQ_WARPS + warp;
+  const int j0 = task * G;                                 // first query of this warp
+  const int nq = max(0, min(G, m - j0));
   const int nslots = nq * S;
-  int *s_idx = reinterpret_cast<int *>(qg_smem);
-  float *s_q = reinterpret_cast<float *>(s_idx + P.qt * S);
-  int *s_cnt = reinterpret_cast<int *>(s_q + P.qt * 3);
-  int *s_first = s_cnt + P.qt;
-  uint8_t *p8 = reinterpret_cast<uint8_t *>(s_first + P.qt);
-  p8 = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(p8) + 15) & ~uintptr_t(15));
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(p8);
-  p8 += 16;
-  float *s_cloud = reinterpret_cast<float *>(p8);
-  int *s_hits = reinterpret_cast<int *>(p8);
-  p8 += P.gs ? BQ_WARPS * GRID_CAP * 4 : P.cloud_floats * 4;
-  p8 = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(p8) + 127) & ~uintptr_t(127));
-  uint8_t *s_tiles = p8;
+  const uint32_t sm0 = umma::smem_u32(qg_smem);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(qg_smem);
+  const uint32_t cloud = sm0 + 16;
+  const uint32_t area1 = P.gs ? (uint32_t)(BQ_WARPS * GRID_CAP * 4) : (uint32_t)P.cloud_pts * 12u;
+  const uint32_t idx_a = sm0 + 16 + ((area1 + 15u) & ~15u) + (uint32_t)warp * (uint32_t)(G * S) * 4u;
+  const uint32_t idx_end = sm0 + 16 + ((area1 + 15u) & ~15u) + (uint32_t)BQ_WARPS * (uint32_t)(G * S) * 4u;
+  const uint32_t tile = ((idx_end + 127u) & ~127u) + (uint32_t)warp * (2 * QG_TILE);  // two 4-KB buffers per warp
 
   const float *xyz = P.xyz + (size_t)b * n * 3;
   const float *new_xyz = P.new_xyz + (size_t)b * m * 3;
   const float radius2 = __fmul_rn(P.radius, P.radius);
-  for (int e = threadIdx.x; e < nq * 3; e += BQ_THREADS) s_q[e] = __ldg(new_xyz + (size_t)j0 * 3 + e);
-  if (threadIdx.x == 0) { umma::mbar_init(s_bar, 1); umma::fence_barrier_init(); }
-  __syncthreads();
+  float qx[QG_MAX_G], qy[QG_MAX_G], qz[QG_MAX_G];
+#pragma unroll
+  for (int g = 0; g < QG_MAX_G; ++g) {
+    const bool v = g < nq;
+    qx[g] = v ? __ldg(new_xyz + (size_t)(j0 + g) * 3) : 0.f;
+    qy[g] = v ? __ldg(new_xyz + (size_t)(j0 + g) * 3 + 1) : 0.f;
+    qz[g] = v ? __ldg(new_xyz + (size_t)(j0 + g) * 3 + 2) : 0.f;
+  }
 
-  // ---------------- phase 1: ball query -> s_idx
+  // ---------------- phase 1: ball query -> this warp's index rows (shared)
+  bool staged_all = false;
   if (P.gs) {
     const GridScene g = P.gs[b];
-    for (int q = warp; q < nq; q += BQ_WARPS) {
-      const float qx = s_q[q * 3], qy = s_q[q * 3 + 1], qz = s_q[q * 3 + 2];
-      int *row = s_idx + q * S;
+    const uint32_t hits = cloud + (uint32_t)warp * GRID_CAP * 4u;
+#pragma unroll
+    for (int gq = 0; gq < QG_MAX_G; ++gq) {
+      if (gq >= nq) break;
+      const uint32_t row = idx_a + (uint32_t)(gq * S) * 4u;
       int first = 0, cnt = -1;
       if (S <= GRID_CAP / 2)
-        cnt = ball_scan_grid(P.gsorted + (size_t)b * n, g, P.gstart + (size_t)b * (GRID_NC + 1), qx, qy, qz, radius2, S,
-                             lane, s_hits + warp * GRID_CAP, row, first);
+        cnt = ball_scan_grid(P.gsorted + (size_t)b * n, g, P.gstart + (size_t)b * (GRID_NC + 1), qx[gq], qy[gq], qz[gq],
+                             radius2, S, lane, hits, first, [&](int pos, int k) { sts_s32(row + 4u * pos, k); });
       if (cnt < 0)
-        cnt = ball_scan(xyz, n, qx, qy, qz, radius2, S, lane, first, [&](int pos, int k) { row[pos] = k; });
+        cnt = ball_scan(xyz, n, qx[gq], qy[gq], qz[gq], radius2, S, lane, first,
+                        [&](int pos, int k) { sts_s32(row + 4u * pos, k); });
       const int fill = cnt == 0 ? 0 : first;
-      for (int l = cnt + lane; l < S; l += 32) row[l] = fill;
+      for (int l = cnt + lane; l < S; l += 32) sts_s32(row + 4u * l, fill);
     }
   } else {
-    for (int q = threadIdx.x; q < nq; q += BQ_THREADS) { s_cnt[q] = 0; s_first[q] = 0; }
-    const int chunk = P.cloud_floats / 3;
+    if (threadIdx.x == 0) { umma::mbar_init(s_bar, 1); umma::fence_barrier_init(); }
+    int cnt[QG_MAX_G], first[QG_MAX_G];
+#pragma unroll
+    for (int g = 0; g < QG_MAX_G; ++g) { cnt[g] = 0; first[g] = 0; }
+    const int chunk = P.cloud_pts;
+    staged_all = n <= chunk;
     uint32_t parity = 0;
+    float *s_cloud = reinterpret_cast<float *>(qg_smem + 16);
     for (int k0 = 0; k0 < n; k0 += chunk) {
       const int np = min(chunk, n - k0);
+      const int np_pad = (np + 127) & ~127;
       const float *src = xyz + (size_t)k0 * 3;
-      // stage the chunk: one bulk (TMA) copy when the source is 16-byte aligned, plus a <= 12-byte tail
+      // stage the chunk: one bulk (TMA) copy when the source is 16-byte aligned, plus the unaligned tail and NaN padding
       const uint32_t bytes = (uint32_t)np * 12u;
       const bool bulk = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && bytes >= 16;
       const uint32_t bulk_bytes = bulk ? (bytes & ~15u) : 0u;
-      __syncthreads();  // previous chunk fully consumed (and s_cnt initialised)
-      if (bulk) {
-        if (threadIdx.x == 0) {
-          umma::fence_proxy_async_smem();  // earlier generic-proxy accesses of the staging area vs the async-proxy write
-          umma::mbar_arrive_expect_tx(s_bar, bulk_bytes);
-          umma::bulk_g2s(s_cloud, src, bulk_bytes, s_bar);
-        }
+      __syncthreads();  // barrier initialised / previous chunk fully consumed
+      if (bulk && threadIdx.x == 0) {
+        umma::fence_proxy_async_smem();  // earlier generic-proxy accesses of the staging area vs the async-proxy write
+        umma::mbar_arrive_expect_tx(s_bar, bulk_bytes);
+        umma::bulk_g2s(s_cloud, src, bulk_bytes, s_bar);
       }
-      for (int e = (int)(bulk_bytes >> 2) + threadIdx.x; e < np * 3; e += BQ_THREADS) s_cloud[e] = __ldg(src + e);
+      for (int e = (int)(bulk_bytes >> 2) + threadIdx.x; e < np_pad * 3; e += BQ_THREADS)
+        s_cloud[e] = e < np * 3 ? __ldg(src + e) : NAN;
       if (bulk) { umma::mbar_wait(s_bar, parity); parity ^= 1u; }
       __syncthreads();
-      for (int q = warp; q < nq; q += BQ_WARPS) {
-        int cnt = s_cnt[q], first = s_first[q];
-        if (cnt >= S) continue;
-        int *row = s_idx + q * S;
-        cnt = ball_scan_smem(s_cloud, np, k0, s_q[q * 3], s_q[q * 3 + 1], s_q[q * 3 + 2], radius2, S, lane, cnt, first,
-                             [&](int pos, int k) { row[pos] = k; });
-        __syncwarp();
-        if (lane == 0) { s_cnt[q] = cnt; s_first[q] = first; }
+#pragma unroll
+      for (int g = 0; g < QG_MAX_G; ++g)
+        if (g < nq)
+          ball_scan_staged(cloud, np_pad, k0, qx[g], qy[g], qz[g], radius2, S, lane, idx_a + (uint32_t)(g * S) * 4u, cnt[g],
+                           first[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < QG_MAX_G; ++g)
+      if (g < nq) {
+        const int c = min(cnt[g], S);
+        const int fill = c == 0 ? 0 : first[g];
+        for (int l = c + lane; l < S; l += 32) sts_s32(idx_a + (uint32_t)(g * S + l) * 4u, fill);
       }
-    }
-    __syncthreads();
-    for (int q = warp; q < nq; q += BQ_WARPS) {
-      const int cnt = min(s_cnt[q], S);
-      const int fill = cnt == 0 ? 0 : s_first[q];
-      for (int l = cnt + lane; l < S; l += 32) s_idx[q * S + l] = fill;
-    }
   }
-  __syncthreads();
+  __syncwarp();
+  if (nslots == 0) return;
 
   const size_t MS = (size_t)m * S;
-  const size_t slot_base = (size_t)j0 * S;  // first (query, sample) slot of this CTA inside a channel plane
+  const size_t slot_base = (size_t)j0 * S;  // first (query, sample) slot of this warp inside a channel plane
   if (P.idx_out) {
     int *dst = P.idx_out + (size_t)b * MS + slot_base;
-    for (int e = threadIdx.x; e < nslots; e += BQ_THREADS) dst[e] = s_idx[e];
+    for (int e = lane; e < nslots; e += 32) dst[e] = lds_s32(idx_a + 4u * e);
   }
   const int cx = P.use_xyz ? 3 : 0;
   const int Ct = cx + P.C;
@@ -487,16 +593,25 @@ query_and_group_kernel(const QgParams P) {
     // torch lowers `tensor /= python_float` on CUDA to a multiply with the f32 reciprocal (pointnet2_utils.py:337)
     const float inv_r = P.normalize_xyz ? __frcp_rn(P.radius) : 1.0f;
     float *gx = P.grouped_xyz ? P.grouped_xyz + (size_t)b * 3 * MS + slot_base : nullptr;
-    for (int e = threadIdx.x; e < nslots; e += BQ_THREADS) {
+    for (int e = lane; e < nslots; e += 32) {
       const int q = P.s_shift >= 0 ? (e >> P.s_shift) : e / S;
-      const int k = s_idx[e];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float v = __fsub_rn(__ldg(xyz + (size_t)k * 3 + c), s_q[q * 3 + c]);  // :335 grouped_xyz -= new_xyz
-        if (P.normalize_xyz) v = __fmul_rn(v, inv_r);                          // :337
-        if (P.use_xyz) out[(size_t)c * MS + e] = v;
-        if (gx) gx[(size_t)c * MS + e] = v;
+      const int k = lds_s32(idx_a + 4u * e);
+      float px, py, pz;
+      if (staged_all) {
+        const uint32_t a = cloud + (uint32_t)k * 12u;
+        asm volatile("ld.shared.f32 %0, [%3];\n\tld.shared.f32 %1, [%3+4];\n\tld.shared.f32 %2, [%3+8];"
+                     : "=f"(px), "=f"(py), "=f"(pz) : "r"(a));
+      } else {
+        px = __ldg(xyz + (size_t)k * 3); py = __ldg(xyz + (size_t)k * 3 + 1); pz = __ldg(xyz + (size_t)k * 3 + 2);
       }
+      float cxq = qx[0], cyq = qy[0], czq = qz[0];
+#pragma unroll
+      for (int g = 1; g < QG_MAX_G; ++g)
+        if (q == g) { cxq = qx[g]; cyq = qy[g]; czq = qz[g]; }
+      float v0 = __fsub_rn(px, cxq), v1 = __fsub_rn(py, cyq), v2 = __fsub_rn(pz, czq);  // :335 grouped_xyz -= new_xyz
+      if (P.normalize_xyz) { v0 = __fmul_rn(v0, inv_r); v1 = __fmul_rn(v1, inv_r); v2 = __fmul_rn(v2, inv_r); }  // :337
+      if (P.use_xyz) { out[e] = v0; out[MS + e] = v1; out[2 * MS + e] = v2; }
+      if (gx) { gx[e] = v0; gx[MS + e] = v1; gx[2 * MS + e] = v2; }
     }
   }
   // ---------------- phase 3: feature channels  out[b][cx+c][j][s] = features[b][c][idx]
@@ -504,54 +619,78 @@ query_and_group_kernel(const QgParams P) {
     float *o = out + (size_t)cx * MS;
     if (!P.feat_t) {
       const float *f = P.features + (size_t)b * P.C * n;
-      for (int e = threadIdx.x; e < nslots; e += BQ_THREADS) {
-        const int k = s_idx[e];
+      for (int e = lane; e < nslots; e += 32) {
+        const int k = lds_s32(idx_a + 4u * e);
         for (int c = 0; c < P.C; ++c) o[(size_t)c * MS + e] = __ldg(f + (size_t)c * n + k);
       }
     } else {
       const int Cp = P.Cp, C = P.C;
       const float *ft = P.feat_t + (size_t)b * n * Cp;
-      const uint32_t tile = umma::smem_u32(s_tiles + warp * QG_TILE);
       const int rsub = lane >> 3, jl = lane & 7;
+      // shared-memory addresses inside a 4-KB transposition buffer (XOR swizzle of the 16-byte chunk index with the row)
+      const uint32_t st_even = rsub * 128 + ((jl ^ rsub) << 4);        // rows 4i + rsub, i even: row & 7 = rsub
+      const uint32_t st_odd = rsub * 128 + ((jl ^ (4 + rsub)) << 4);   // i odd: row & 7 = 4 + rsub
+      const uint32_t ld_off = lane * 128 + ((lane & 7) << 4);          // chunk j of row `lane` at ld_off ^ (j << 4)
       const int ntile = (nslots + 31) >> 5;
-      for (int t = warp; t < ntile; t += BQ_WARPS) {
-        const int slot0 = t * 32;
-        const float *rowp[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int slot = slot0 + 4 * i + rsub;
-          rowp[i] = slot < nslots ? ft + (size_t)s_idx[slot] * Cp + 4 * jl : nullptr;
-        }
-        const int myslot = slot0 + lane;
-        const bool sv = myslot < nslots;
-        float *om = o + myslot;
-        for (int c0 = 0; c0 < Cp; c0 += 32) {
-          const bool cv = c0 + 4 * jl < Cp;
-          float4 v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            v[i] = (cv && rowp[i]) ? __ldg(reinterpret_cast<const float4 *>(rowp[i] + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int nc0 = (Cp + 31) >> 5;
+      const int nit = ntile * nc0;
+      // The gathered rows go global -> shared with cp.async (L2 only, no registers), two (tile, 32-channel) steps in
+      // flight per warp: the loads of step it+1 are issued before step it is transposed out, hiding the L2 latency.
+      auto issue = [&](int it) {
+        const int t = it / nc0, c0 = (it - t * nc0) << 5;
+        const uint32_t buf = tile + (uint32_t)(it & 1) * QG_TILE;
+        if (c0 + 4 * jl < Cp) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + rsub;
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile + r * 128 + ((jl ^ (r & 7)) << 4)),
-                         "f"(v[i].x), "f"(v[i].y), "f"(v[i].z), "f"(v[i].w)
-                         : "memory");
-          }
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 w = umma::lds_f4(tile + lane * 128 + ((j ^ (lane & 7)) << 4));
-            const int ch = c0 + 4 * j;
-            if (sv) {
-              if (ch < C) om[(size_t)ch * MS] = w.x;
-              if (ch + 1 < C) om[(size_t)(ch + 1) * MS] = w.y;
-              if (ch + 2 < C) om[(size_t)(ch + 2) * MS] = w.z;
-              if (ch + 3 < C) om[(size_t)(ch + 3) * MS] = w.w;
+            const int slot = t * 32 + 4 * i + rsub;
+            if (slot < nslots) {
+              const float *src = ft + (size_t)((uint32_t)lds_s32(idx_a + 4u * slot) * (uint32_t)Cp) + c0 + 4 * jl;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(buf + ((i & 1) ? st_odd : st_even) + i * 512), "l"(src)
+                           : "memory");
             }
           }
-          __syncwarp();
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      issue(0);
+      for (int it = 0; it < nit; ++it) {
+        if (it + 1 < nit) {
+          issue(it + 1);
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        const int t = it / nc0, c0 = (it - t * nc0) << 5;
+        const uint32_t ld_base = tile + (uint32_t)(it & 1) * QG_TILE + ld_off;
+        const int myslot = t * 32 + lane;
+        const bool sv = myslot < nslots;
+        float *oc = o + (size_t)c0 * MS + myslot;
+        if (t * 32 + 32 <= nslots && c0 + 32 <= C) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w = lds128(ld_base ^ (uint32_t)(j << 4));
+            oc[0] = w.x; oc += MS;
+            oc[0] = w.y; oc += MS;
+            oc[0] = w.z; oc += MS;
+            oc[0] = w.w; oc += MS;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w = lds128(ld_base ^ (uint32_t)(j << 4));
+            const int ch = c0 + 4 * j;
+            if (sv && ch < C) oc[0] = w.x;
+            oc += MS;
+            if (sv && ch + 1 < C) oc[0] = w.y;
+            oc += MS;
+            if (sv && ch + 2 < C) oc[0] = w.z;
+            oc += MS;
+            if (sv && ch + 3 < C) oc[0] = w.w;
+            oc += MS;
+          }
+        }
+        __syncwarp();  // the buffer is free for the loads of step it + 2
       }
     }
   }
@@ -705,14 +844,14 @@ extern "C" int rfd_query_and_group(const float *xyz, const float *new_xyz, const
   P.use_xyz = use_xyz; P.normalize_xyz = normalize_xyz;
   P.new_features = new_features; P.grouped_xyz = grouped_xyz; P.idx_out = idx;
   P.s_shift = (nsample & (nsample - 1)) == 0 ? __builtin_ctz((unsigned)nsample) : -1;
-  // queries per CTA: >= 8 (one per warp in phase 1), ~256 slots, never more than QG_MAX_SLOTS
-  int qt = nsample >= 256 ? QG_MAX_SLOTS / nsample : 256 / nsample;
-  if (nsample < 256 && qt < BQ_WARPS) qt = BQ_WARPS;
-  if (qt < 1) qt = 1;
-  if (qt > M) qt = M;
-  P.qt = qt;
+  // queries per warp task: enough to fill a 32-slot tile (nsample < 32), never more than QG_MAX_G
+  int G = nsample >= 32 ? 1 : 32 / nsample;
+  if (G > QG_MAX_G) G = QG_MAX_G;
+  if (G < 1) G = 1;
+  P.G = G;
   const bool use_grid = N >= GRID_MIN_N && radius > 0.f;
-  const bool transposed = C >= 8;  // below that the direct 4-byte gathers are cheaper than the extra pass
+  // the point-major copy is worth its pass from 8 channels on; its 32-bit row offsets need N * Cp < 2^32
+  const bool transposed = C >= 8 && (unsigned long long)N * (unsigned long long)((C + 3) & ~3) < 0xffffffffull;
   P.Cp = transposed ? (C + 3) & ~3 : 0;
   GridPtrs g;
   const int rc = prepare(xyz, B, N, radius, use_grid, transposed ? sizeof(float) * (size_t)B * N * P.Cp : 0, st, &g);
@@ -724,13 +863,14 @@ extern "C" int rfd_query_and_group(const float *xyz, const float *new_xyz, const
     transpose_features_kernel<<<tg, 256, 0, st>>>(features, C, N, P.Cp, g.feat_t);
     RFD_CHECK_LAUNCH("transpose_features_kernel");
   }
-  P.cloud_floats = use_grid ? 0 : 3 * (N < QG_CHUNK ? ((N + 3) & ~3) : QG_CHUNK);
-  size_t smem = (size_t)qt * nsample * 4 + (size_t)qt * 3 * 4 + (size_t)qt * 8 + 16 + 16;
-  smem += use_grid ? (size_t)BQ_WARPS * GRID_CAP * 4 : (size_t)P.cloud_floats * 4;
-  smem += 128 + (transposed ? (size_t)BQ_WARPS * QG_TILE : 0);
+  P.cloud_pts = use_grid ? 0 : (N < QG_CHUNK ? ((N + 127) & ~127) : QG_CHUNK);
+  size_t smem = 16 + (((use_grid ? (size_t)BQ_WARPS * GRID_CAP * 4 : (size_t)P.cloud_pts * 12) + 15) & ~(size_t)15);
+  smem += (size_t)BQ_WARPS * G * nsample * 4;
+  smem += 128 + (transposed ? (size_t)BQ_WARPS * 2 * QG_TILE : 0);
   RFD_CHECK_CUDA(cudaFuncSetAttribute(query_and_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024),
                  "query_and_group attr");
-  dim3 grid(h_ceil_div(M, qt), B);
+  const int tasks = h_ceil_div(M, G);
+  dim3 grid(h_ceil_div(tasks, BQ_WARPS), B);
   query_and_group_kernel<<<grid, BQ_THREADS, smem, st>>>(P);
   RFD_CHECK_LAUNCH("query_and_group_kernel");
   return RFD_OK;

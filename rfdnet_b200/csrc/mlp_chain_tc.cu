@@ -559,6 +559,9 @@ static ChainPlan chain_plan(int mode, int K0, int xyz, int C1, int C2, int C3) {
       for (int c0 = 0; c0 < n; c0 += 256) {
         if (p.nsteps >= CH_MAX_STEPS) return p;
         const int nv = n - c0 < 256 ? n - c0 : 256;
+        // a second column block re-reads the RESIDENT A panels: its K must fit in them (layer 0 with K0 > 256 streams
+        // through the panels in rounds and is gone by then)
+        if (c0 > 0 && (k + 63) / 64 > CH_APAN) return p;
         ChainStep &s = p.st[p.nsteps];
         s = ChainStep{(k + 63) / 64, (nv + 15) & ~15, 1, 1, c0 > 0 ? 1 : 0, c0, nv, tab};
         p.k_valid[p.nsteps] = k; p.layer[p.nsteps] = l; p.row0[p.nsteps] = c0;

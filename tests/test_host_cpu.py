@@ -34,6 +34,11 @@ def test_cabi_exports_every_declared_symbol(lib):
     assert lib.rfd_onet_packed_bytes(1) == 10 * 4 * 256 * 128 == lib.rfd_onet_packed_bytes(2)
     assert lib.rfd_onet_packed_bytes(3) == 2 * 10 * 4 * 256 * 128
     assert lib.rfd_onet_aff_floats() == 2 * 11 * 2 * 256 + 256
+    # chain-MLP plan (host-only): supported shapes report their packed size, unsupported ones 0
+    assert lib.rfd_mlp_chain_packed_bytes(3, 512, 0, 256, 256, 0) > 0        # FP module, K0 streams in two rounds
+    assert lib.rfd_mlp_chain_packed_bytes(3, 200, 0, 512, 0, 0) > 0          # one layer, two column blocks
+    assert lib.rfd_mlp_chain_packed_bytes(3, 300, 0, 512, 0, 0) == 0         # second block would need non-resident A
+    assert lib.rfd_mlp_chain_packed_bytes(3, 64, 0, 300, 64, 0) == 0         # hidden layer wider than 256
 
 
 def test_no_oracle_import_in_product():
@@ -181,6 +186,55 @@ assert t == float(world)
 D.barrier()
 sys.stdout.write("rank" + str(rank) + "-ok\n"); sys.stdout.flush()
 """
+
+
+_GLOO_BUCKETS_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, %r)
+from rfdnet_b200 import dist as D
+from rfdnet_b200.train import GradBuckets
+rank, world, _ = D.init_from_env("gloo")
+torch.manual_seed(0)
+def make():
+    return torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 9), torch.nn.ReLU(),
+                               torch.nn.Linear(9, 1), torch.nn.Linear(1, 1))
+net = make()
+unused = torch.nn.Parameter(torch.ones(3))            # a parameter that never receives a gradient
+data = torch.randn(8, 6); tgt = torch.randn(8, 1)
+buckets = GradBuckets(list(net.parameters()) + [unused], bucket_bytes=64)    # tiny buckets: several per step
+assert len(buckets.buckets) >= 3
+net2 = make(); net2.load_state_dict(net.state_dict())
+lo, hi = D.shard_range(8, rank, world)
+for step in range(2):                                   # twice: counters / views must re-arm
+    buckets.zero()
+    loss = ((net(data[lo:hi]) - tgt[lo:hi]) ** 2).sum() / 8 * world
+    loss.backward()                                     # hooks launch the per-bucket all-reduces during backward
+    buckets.finish()
+    net2.zero_grad(set_to_none=True)
+    (((net2(data) - tgt) ** 2).sum() / 8).backward()
+    for a, b in zip(net.parameters(), net2.parameters()):
+        assert torch.allclose(a.grad, b.grad, atol=1e-6), (a.grad, b.grad)
+    assert float(unused.grad.abs().sum()) == 0.0
+assert buckets.nbytes == (sum(p.numel() for p in net.parameters()) + 3) * 4
+# gradients are views into the flat buckets (no flatten / copy-back)
+b0 = buckets.buckets[0]
+assert b0["params"][0].grad.data_ptr() == b0["buf"].data_ptr()
+D.barrier()
+sys.stdout.write("rank" + str(rank) + "-ok\n"); sys.stdout.flush()
+"""
+
+
+@pytest.mark.timeout(300)
+def test_gloo_world2_bucketed_overlapped_allreduce(tmp_path):
+    """GradBuckets (rfdnet_b200/train.py): the averaged 2-rank gradients equal the single-process full-batch gradients."""
+    script = tmp_path / "worker_b.py"
+    script.write_text(_GLOO_BUCKETS_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, env=env, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("-ok") == 2, r.stdout
 
 
 @pytest.mark.timeout(300)

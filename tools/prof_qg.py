@@ -9,6 +9,7 @@ import json
 
 import torch
 
+from bench import graph_time
 from rfdnet_b200 import pointnet2_utils as pu
 from rfdnet_b200.synth import scannet_like_batch
 
@@ -38,16 +39,13 @@ for name, src, q, r, S, C in shapes:
     N, M = src.shape[1], q.shape[1]
     g = torch.Generator(device=dev).manual_seed(1)
     feats = torch.randn(B, C, N, device=dev, generator=g)
-    for _ in range(3):
-        out, _, _ = pu.fused_query_and_group(src, q, feats, r, S, True, True)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(ITERS):
-        out, _, _ = pu.fused_query_and_group(src, q, feats, r, S, True, True)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / ITERS
+    if ITERS > 1:
+        ms = graph_time(lambda: pu.fused_query_and_group(src, q, feats, r, S, True, True), ITERS)
+    else:
+        for _ in range(4):
+            pu.fused_query_and_group(src, q, feats, r, S, True, True)
+        torch.cuda.synchronize()
+        ms = 1.0
     nbytes = B * (12 * N + 12 * M + 4 * C * N + 4 * (3 + C) * M * S)
     gbs = nbytes / (ms * 1e-3) / 1e9
     tot_b += nbytes
