@@ -248,6 +248,18 @@ def run_gpu(args, rank, world, local):
     D.barrier()
     t_e2e = D.max_over_ranks(t_e2e, dev)
 
+    # ---- BASELINE config 5: training step with the NCCL gradient all-reduce (every rank takes part)
+    train = None
+    if not args.no_train:
+        try:
+            train = train_bench(args, rank, world, dev)
+        except Exception as e:  # the inference line must survive a failure of the training block
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            train = {"error": repr(e)[:300]}
+            if world > 1:
+                raise
+
     if rank != 0:
         return
     # ---- per-kernel device times (CUDA events recorded around the launches inside the timed steps)
@@ -310,8 +322,81 @@ def run_gpu(args, rank, world, local):
                 "ms_per_step": t_e2e / args.steps * 1e3},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "train": train,
     }
     print(json.dumps(line))
+
+
+def train_bench(args, rank, world, dev):
+    """BASELINE config 5: the joint ISCNet training step (detection + SkipPropagation + ONet encoder/decoder in train
+    mode, Adam) on `--train-batch` synthetic 80k-point scenes PER GPU, gradients exchanged by the bucketed NCCL all-reduce
+    launched from autograd hooks while backward is still running (rfdnet_b200/train.py).  All times are CUDA-event
+    times, max over ranks.
+      ms_per_step        whole step (zero, forward, backward + overlapped all-reduce, optimizer)
+      allreduce_us       the same buckets all-reduced back to back on an otherwise idle GPU (no overlap possible)
+      bus_gbs            2 (N-1)/N x bytes / allreduce_us  (ring/NVLS bus bandwidth convention)
+      exposed_us         in-step time between the last backward kernel and the completion of the last bucket
+      overlap_frac       1 - exposed / allreduce  (share of the exchange hidden under backward)"""
+    from rfdnet_b200 import dist as D, train as T
+    from rfdnet_b200.synth import scannet_like_batch, seeded_fill
+    B, K, Tpts = args.train_batch, 10, 2048
+    torch.manual_seed(1234 + rank)
+    model = T.JointTrainStep(boxes_per_scene=K)
+    seeded_fill(model, 11)
+    model = model.to(dev).train()
+    pc = torch.from_numpy(scannet_like_batch(B, 80000, seed0=5000 + 100 * rank)).to(dev)
+    lab = T.synthetic_labels(B, 80000, K, Tpts, dev, seed=rank)
+    trainer = T.Trainer(model, bucket_bytes=args.bucket_mb << 20)
+    losses = []
+    for _ in range(2):
+        loss, _ = trainer.step(pc, lab)
+        losses.append(float(loss))
+    torch.cuda.synchronize()
+    D.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    exposed = []
+    e0.record()
+    for _ in range(args.train_steps):
+        loss, _ = trainer.step(pc, lab, record=True)
+        exposed.append(trainer.ev)
+    e1.record()
+    torch.cuda.synchronize()
+    D.barrier()
+    losses.append(float(loss))
+    ms = D.max_over_ranks(e0.elapsed_time(e1) / args.train_steps, dev)
+    exposed_us = D.max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in exposed])) * 1e3, dev)
+    nbytes = trainer.buckets.nbytes
+    ar_us = None
+    if world > 1:
+        for _ in range(2):
+            trainer.buckets.allreduce_only()
+        torch.cuda.synchronize()
+        D.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            trainer.buckets.allreduce_only()
+        a1.record()
+        torch.cuda.synchronize()
+        ar_us = D.max_over_ranks(a0.elapsed_time(a1) / 5 * 1e3, dev)
+    finite = all(np.isfinite(losses))
+    out = {"workload": "joint ISCNet train step (BASELINE config 5): detection (train-mode BN) + SkipPropagation "
+                       "(STN_Group r=1.0/nsample=1024 + PointSeg + ResnetPointnet) + ONet Encoder_Latent/batch-stat CBN "
+                       "decoder (KL + BCE) + Adam; point-cloud ops and their scatter-add grads = librfdnet_b200, dense "
+                       "layers = PyTorch library GEMMs; surrogate detection loss (models/loss.py is out of scope)",
+           "scenes_per_gpu": B, "points": 80000, "boxes_per_scene": K, "occ_points_per_box": Tpts,
+           "ms_per_step": ms, "scenes_per_s": world * B / (ms * 1e-3), "steps": args.train_steps, "warmup": 2,
+           "params": sum(p.numel() for p in model.parameters()), "allreduce_bytes": nbytes,
+           "buckets": len(trainer.buckets.buckets), "bucket_mb": args.bucket_mb,
+           "allreduce_us": ar_us, "bus_gbs": (2.0 * (world - 1) / world * nbytes / (ar_us * 1e-6) / 1e9) if ar_us else None,
+           "nvlink_peak_gbs": 900.0, "exposed_us": exposed_us if world > 1 else 0.0,
+           "overlap_frac": (max(0.0, 1.0 - exposed_us / ar_us) if ar_us else None),
+           "loss_first_last": [losses[0], losses[-1]], "loss_finite": bool(finite),
+           "collective": "nccl all_reduce(AVG) per bucket, async from post-accumulate-grad hooks" if world > 1 else "none (1 GPU)"}
+    del trainer, model
+    torch.cuda.empty_cache()
+    return out
 
 
 def graph_time(fn, iters, reps=3):
@@ -389,6 +474,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=4, help="scenes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-5 training-step block")
+    ap.add_argument("--train-batch", type=int, default=8, help="scenes per GPU per training step (config 5: 8)")
+    ap.add_argument("--train-steps", type=int, default=3)
+    ap.add_argument("--bucket-mb", type=int, default=8, help="gradient all-reduce bucket size")
     ap.add_argument("--backbone-precision", default="x3", choices=["x3", "fp16", "bf16", "cuda"],
                     help="MLPs of SA1-4 / FP1-2 (BASELINE config 2 is fp32): x3 = split-fp16 tcgen05, fp32-grade (default); "
                          "fp16 / bf16 = single-MMA tcgen05; cuda = fp32 CUDA-core layer kernel")

@@ -50,6 +50,11 @@ def pointwise_layer(x, W, scale, shift, relu, pool=1, residual=None):
     B, Cin, L = x.shape
     Cout = W.shape[0]
     assert W.shape[1] == Cin and W.device == x.device, (W.shape, Cin)
+    if pool > 64 and pool % 64 == 0:
+        # the kernel pools inside its 64-position tile; wider groups (STN_Group-sized nsample) finish with one reduction
+        # over the per-tile maxima
+        y = pointwise_layer(x, W, scale, shift, relu, pool=64, residual=residual)
+        return y.view(B, Cout, L // pool, pool // 64).amax(dim=-1)
     y = torch.empty((B, Cout, L // pool), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().rfd_pointwise_mlp_f32(
