@@ -516,6 +516,8 @@ def main():
         os.close(saved_stdout)
     run_gpu(args, rank, world, local)
     if world > 1:
+        sys.stdout.flush()
+        os.dup2(2, 1)  # NCCL_DEBUG=INFO also logs the communicator teardown on stdout: keep it behind the JSON line
         torch.distributed.destroy_process_group()
 
 
