@@ -24,6 +24,7 @@
 //            through XOR-swizzled shared memory (conflict-free 16-byte stores and loads) and writes each channel's
 //            32 consecutive slots as one 128-byte coalesced store.  No per-element index arithmetic, no div/mod.
 // None of the reference's four intermediate passes over the grouped tensor exists.
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -103,13 +104,17 @@ constexpr int GRID_G = 32;                        // max cells per axis
 constexpr int GRID_NC = GRID_G * GRID_G * GRID_G;  // 32768
 constexpr int GRID_CAP = 512;                      // hits kept per query before falling back
 constexpr int GRID_MIN_N = 8192;                   // use the grid from this cloud size on
-constexpr int GB_CS = 8;                           // grid build: CTAs per scene (one thread-block cluster)
-constexpr int GB_THREADS = 1024;
+constexpr int GB_THREADS = 1024;                   // grid build: one thread-block cluster of CS (8 or 16) CTAs per scene
 
 struct GridScene {
   float ox, oy, oz, inv_cell;
   int gx, gy, gz, pad;
 };
+
+// programmatic dependent launch (PDL): the producer kernel lets its dependent be scheduled early; the dependent runs its
+// independent prologue and blocks at pdl_wait() until the producer grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
@@ -148,12 +153,14 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 // points of a round as one batch -- all loads, then all atomics, then all stores, the cells kept in registers between
 // the phases -- so the kernel is bound by three cluster barriers and one L2 round trip per phase, not by per-point
 // latencies.
-constexpr int GB_PPT = 10;  // points per thread per round (8192 threads x 10 = 81920 points per round)
+constexpr int GB_PPT = 5;  // points per thread per round (16 CTAs x 1024 threads x 5 = 81920 points per round)
 
-__global__ void __cluster_dims__(GB_CS, 1, 1) __launch_bounds__(GB_THREADS, 1)
+template <int GB_CS>
+__global__ void __launch_bounds__(GB_THREADS, 1)
 grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridScene *__restrict__ gs,
                   int *__restrict__ count, int *__restrict__ start, float4 *__restrict__ sorted) {
   extern __shared__ int s_start[];  // GRID_NC
+  pdl_launch_dependents();  // the query kernel may be scheduled now; it waits (griddepcontrol.wait) before touching the grid
   __shared__ int s_bbox[6], s_box[6];
   __shared__ int s_wsum[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -246,28 +253,31 @@ grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridScene 
       if (cellv[i] >= 0) atomicAdd(count + cellv[i], 1);
   }
   umma::cluster_sync();
-  // ---- 2: exclusive scan (warp w owns cells [1024 w, 1024 w + 1024))
+  // ---- 2: exclusive scan of the ncell valid cells (warp w owns `per` rows of 32 consecutive cells)
   const int ncell = g.gx * g.gy * g.gz;
   {
-    constexpr int PER = GRID_NC / 32 / 32;  // 32 coalesced rows of 32 cells per warp
-    const int c0 = warp * (GRID_NC / 32);
+    constexpr int PER = GRID_NC / 32 / 32;             // 32 rows per warp cover the largest grid
+    const int per = (ncell + 1023) >> 10;              // rows per warp for THIS grid (warp-uniform, <= PER)
+    const int c0 = warp * per * 32;
     int v[PER];
 #pragma unroll
     for (int it = 0; it < PER; ++it) {
       const int c = c0 + it * 32 + lane;
-      v[it] = c < ncell ? __ldcg(count + c) : 0;
+      v[it] = (it < per && c < ncell) ? __ldcg(count + c) : 0;
     }
     int run = 0;
 #pragma unroll
     for (int it = 0; it < PER; ++it) {
-      int inc = v[it];
+      if (it < per) {
+        int inc = v[it];
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, off);
-        if (lane >= off) inc += t;
+        for (int off = 1; off < 32; off <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, off);
+          if (lane >= off) inc += t;
+        }
+        v[it] = run + inc - v[it];
+        run += __shfl_sync(0xffffffffu, inc, 31);
       }
-      v[it] = run + inc - v[it];
-      run += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (lane == 0) s_wsum[warp] = run;
     __syncthreads();
@@ -285,12 +295,14 @@ grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridScene 
     const int woff = s_wsum[warp];
 #pragma unroll
     for (int it = 0; it < PER; ++it) {
-      const int c = c0 + it * 32 + lane;
-      const int val = v[it] + woff;
-      s_start[c] = val;
-      if (rank == 0 && c <= ncell) start[c] = c < ncell ? val : n;
+      if (it < per) {
+        const int c = c0 + it * 32 + lane;
+        const int val = v[it] + woff;
+        if (c < GRID_NC) s_start[c] = val;
+        if (rank == 0 && c <= ncell && c < GRID_NC + 1) start[c] = c < ncell ? val : n;
+      }
     }
-    if (rank == 0 && tid == 0 && ncell == GRID_NC) start[GRID_NC] = n;
+    if (rank == 0 && tid == 0) start[ncell] = n;
   }
   __syncthreads();
   umma::cluster_sync();  // every CTA has read the histogram before anyone starts undoing it
@@ -327,62 +339,137 @@ __device__ __forceinline__ int4 lds_s128(uint32_t a) {
   return v;
 }
 
+// nsample-th smallest of the H (> nsample) distinct ids in hits[] (shared): bisection on the id VALUE with the warp's hits
+// held in registers (K per lane) -- ceil(log2 n) rounds of K compares + one redux.sync, instead of ranking all H hits
+// against each other (H^2 / 32 compares per lane).
+template <int K>
+__device__ __forceinline__ int select_kth_id(uint32_t hits, int H, int nsample, int n, int lane, int (&mine)[K]) {
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const int h = lane + 32 * i;
+    mine[i] = h < H ? lds_s32(hits + 4u * h) : 0x7fffffff;
+  }
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) c += mine[i] <= mid;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= nsample) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// keep the ids <= T (exactly nsample of them), compacted to hits[0, nsample) -- order inside is irrelevant, the ranking
+// below restores it
+template <int K>
+__device__ __forceinline__ void compact_selected(uint32_t hits, int T, int lane, const int (&mine)[K]) {
+  const unsigned lt = (1u << lane) - 1u;
+  int base = 0;
+  __syncwarp();  // every lane has read its hits
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const bool keep = mine[i] <= T;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) sts_s32(hits + 4u * (base + __popc(m & lt)), mine[i]);
+    base += __popc(m);
+  }
+}
+
 // Grid scan for one query by one warp: collects the hits of the 27 neighbouring cells in `hits` (shared-memory address,
-// GRID_CAP ints, 16-byte aligned), ranks them by index and writes the first nsample through `put(rank, id)` in ascending
+// GRID_CAP ints, 16-byte aligned), keeps the nsample smallest ids and writes them through `put(rank, id)` in ascending
 // index order.  Returns the hit count capped at nsample, or -1 if more than GRID_CAP hits were found (caller falls back).
+// The 9 (x, y) cell columns of the neighbourhood are 9 contiguous runs of the sorted array (z is the fastest cell index);
+// lanes 0..8 fetch the run bounds in ONE round trip, then the warp walks the concatenation of the runs 32 candidates at a
+// time (two dependent memory round trips per query instead of eighteen).
 template <typename Put>
 __device__ __forceinline__ int ball_scan_grid(const float4 *__restrict__ sorted, const GridScene &g,
                                               const int *__restrict__ start, float qx, float qy, float qz,
-                                              float radius2, int nsample, int lane, uint32_t hits, int &first, Put put) {
+                                              float radius2, int nsample, int n, int lane, uint32_t hits, int &first,
+                                              Put put) {
   const int cx = grid_coord(qx, g.ox, g.inv_cell, g.gx), cy = grid_coord(qy, g.oy, g.inv_cell, g.gy),
             cz = grid_coord(qz, g.oz, g.inv_cell, g.gz);
+  int beg = 0, len = 0;
+  if (lane < 9) {
+    const int ix = cx - 1 + lane / 3, iy = cy - 1 + lane % 3;
+    const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.gz - 1);
+    if (ix >= 0 && ix < g.gx && iy >= 0 && iy < g.gy && z0 <= z1) {
+      const int c0 = (ix * g.gy + iy) * g.gz;
+      beg = __ldg(start + c0 + z0);
+      len = __ldg(start + c0 + z1 + 1) - beg;
+    }
+  }
+  int rb[9], rd[9];  // run r covers the flattened candidates [rb[r], rb[r+1]); candidate e of run r is sorted[e + rd[r]]
+  int total;
+  {
+    int inc = len;
+#pragma unroll
+    for (int off = 1; off < 16; off <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += t;
+    }
+    const int excl = inc - len;
+    const int delta = beg - excl;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      rb[r] = __shfl_sync(0xffffffffu, excl, r);
+      rd[r] = __shfl_sync(0xffffffffu, delta, r);
+    }
+    total = __shfl_sync(0xffffffffu, inc, 8);
+  }
   int H = 0;
   const unsigned lt = (1u << lane) - 1u;
-  for (int ix = max(cx - 1, 0); ix <= min(cx + 1, g.gx - 1); ++ix)
-    for (int iy = max(cy - 1, 0); iy <= min(cy + 1, g.gy - 1); ++iy) {
-      // cells (ix, iy, z0..z1) are contiguous in the cell order => one contiguous run of the sorted array
-      const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.gz - 1);
-      if (z0 > z1) continue;
-      const int c0 = (ix * g.gy + iy) * g.gz;
-      const int beg = __ldg(start + c0 + z0), end = __ldg(start + c0 + z1 + 1);
-      for (int base = beg; base < end; base += 32) {
-        const int e = base + lane;
-        bool hit = false;
-        int k = 0;
-        if (e < end) {
-          const float4 pt = __ldg(sorted + e);
-          k = __float_as_int(pt.w);
-          hit = sqdist_yxz(qx - pt.x, qy - pt.y, qz - pt.z) < radius2;
-        }
-        const unsigned mask = __ballot_sync(0xffffffffu, hit);
-        if (mask) {
-          const int pos = H + __popc(mask & lt);
-          if (hit && pos < GRID_CAP) sts_s32(hits + 4u * pos, k);
-          H += __popc(mask);
-        }
-      }
+  for (int base = 0; base < total; base += 32) {
+    const int e = base + lane;
+    int d = rd[0];  // rb[] is ascending: the last run that starts at or before e owns it (empty runs never win)
+#pragma unroll
+    for (int r = 1; r < 9; ++r)
+      if (e >= rb[r]) d = rd[r];
+    const int src = e < total ? e + d : -1;
+    bool hit = false;
+    int k = 0;
+    if (src >= 0) {
+      const float4 pt = __ldg(sorted + src);
+      k = __float_as_int(pt.w);
+      hit = sqdist_yxz(qx - pt.x, qy - pt.y, qz - pt.z) < radius2;
     }
+    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+    if (mask) {
+      const int pos = H + __popc(mask & lt);
+      if (hit && pos < GRID_CAP) sts_s32(hits + 4u * pos, k);
+      H += __popc(mask);
+    }
+  }
   if (H > GRID_CAP) return -1;
+  __syncwarp();
+  int nsel = H;
+  if (H > nsample) {
+    if (H <= 128) { int mine[4]; const int T = select_kth_id<4>(hits, H, nsample, n, lane, mine); compact_selected<4>(hits, T, lane, mine); }
+    else if (H <= 256) { int mine[8]; const int T = select_kth_id<8>(hits, H, nsample, n, lane, mine); compact_selected<8>(hits, T, lane, mine); }
+    else { int mine[16]; const int T = select_kth_id<16>(hits, H, nsample, n, lane, mine); compact_selected<16>(hits, T, lane, mine); }
+    nsel = nsample;
+    __syncwarp();
+  }
   // pad to a multiple of 4 with INT_MAX (never smaller than an id) so the ranking can read 16 bytes at a time
-  if (lane < 4 && H + lane < ((H + 3) & ~3)) sts_s32(hits + 4u * (H + lane), 0x7fffffff);
+  const int n4 = (nsel + 3) & ~3;
+  if (lane < 4 && nsel + lane < n4) sts_s32(hits + 4u * (nsel + lane), 0x7fffffff);
   __syncwarp();
   int mn = 0x7fffffff;
-  const int H4 = (H + 3) & ~3;
-  for (int h = lane; h < H; h += 32) {
+  for (int h = lane; h < nsel; h += 32) {
     const int id = lds_s32(hits + 4u * h);
     int rank = 0;
-    for (int t = 0; t < H4; t += 4) {  // every lane reads the same 16 bytes: one broadcast wavefront
+    for (int t = 0; t < n4; t += 4) {  // every lane reads the same 16 bytes: one broadcast wavefront
       const int4 o = lds_s128(hits + 4u * t);
       rank += (o.x < id) + (o.y < id) + (o.z < id) + (o.w < id);
     }
-    if (rank < nsample) put(rank, id);
+    put(rank, id);
     mn = min(mn, id);
   }
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-  first = H ? mn : 0;
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  first = nsel ? mn : 0;
   __syncwarp();
-  return H < nsample ? H : nsample;
+  return nsel;
 }
 
 __global__ void __launch_bounds__(BQ_THREADS)
@@ -402,7 +489,7 @@ ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
   int first, cnt = -1;
   if (gs)
     cnt = ball_scan_grid(gsorted + (size_t)b * n, gs[b], gstart + (size_t)b * (GRID_NC + 1), qx, qy, qz, radius2,
-                         nsample, lane, umma::smem_u32(s_hits[warp]), first, [&](int pos, int k) { row[pos] = k; });
+                         nsample, n, lane, umma::smem_u32(s_hits[warp]), first, [&](int pos, int k) { row[pos] = k; });
   if (cnt < 0)
     cnt = ball_scan(xyz, n, qx, qy, qz, radius2, nsample, lane, first, [&](int pos, int k) { row[pos] = k; });
   // reference :35-39: the first hit pre-fills every slot; no hit at all leaves the zero-initialised row
@@ -414,6 +501,7 @@ ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
 __global__ void __launch_bounds__(256)
 transpose_features_kernel(const float *__restrict__ f, int C, int N, int Cp, float *__restrict__ ft) {
   __shared__ float t[32][33];
+  pdl_launch_dependents();
   const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   f += (size_t)b * C * N;
@@ -519,6 +607,7 @@ query_and_group_kernel(const QgParams P) {
   // ---------------- phase 1: ball query -> this warp's index rows (shared)
   bool staged_all = false;
   if (P.gs) {
+    pdl_wait();  // the grid (and the point-major features) of this call are complete
     const GridScene g = P.gs[b];
     const uint32_t hits = cloud + (uint32_t)warp * GRID_CAP * 4u;
 #pragma unroll
@@ -528,7 +617,7 @@ query_and_group_kernel(const QgParams P) {
       int first = 0, cnt = -1;
       if (S <= GRID_CAP / 2)
         cnt = ball_scan_grid(P.gsorted + (size_t)b * n, g, P.gstart + (size_t)b * (GRID_NC + 1), qx[gq], qy[gq], qz[gq],
-                             radius2, S, lane, hits, first, [&](int pos, int k) { sts_s32(row + 4u * pos, k); });
+                             radius2, S, n, lane, hits, first, [&](int pos, int k) { sts_s32(row + 4u * pos, k); });
       if (cnt < 0)
         cnt = ball_scan(xyz, n, qx[gq], qy[gq], qz[gq], radius2, S, lane, first,
                         [&](int pos, int k) { sts_s32(row + 4u * pos, k); });
@@ -624,6 +713,7 @@ query_and_group_kernel(const QgParams P) {
         for (int c = 0; c < P.C; ++c) o[(size_t)c * MS + e] = __ldg(f + (size_t)c * n + k);
       }
     } else {
+      if (!P.gs) pdl_wait();  // the transposition pass ran concurrently with the search; its output is needed from here on
       const int Cp = P.Cp, C = P.C;
       const float *ft = P.feat_t + (size_t)b * n * Cp;
       const int rsub = lane >> 3, jl = lane & 7;
@@ -636,8 +726,8 @@ query_and_group_kernel(const QgParams P) {
       const int nit = ntile * nc0;
       // The gathered rows go global -> shared with cp.async (L2 only, no registers), two (tile, 32-channel) steps in
       // flight per warp: the loads of step it+1 are issued before step it is transposed out, hiding the L2 latency.
-      auto issue = [&](int it) {
-        const int t = it / nc0, c0 = (it - t * nc0) << 5;
+      // (tile, channel block) of a step advance incrementally (no integer division in the loop)
+      auto issue = [&](int it, int t, int c0) {
         const uint32_t buf = tile + (uint32_t)(it & 1) * QG_TILE;
         if (c0 + 4 * jl < Cp) {
 #pragma unroll
@@ -652,16 +742,18 @@ query_and_group_kernel(const QgParams P) {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       };
-      issue(0);
+      issue(0, 0, 0);
+      int t = 0, c0 = 0;            // step `it`
       for (int it = 0; it < nit; ++it) {
+        int tn = t, cn = c0 + 32;   // step it + 1
+        if (cn >= (nc0 << 5)) { cn = 0; ++tn; }
         if (it + 1 < nit) {
-          issue(it + 1);
+          issue(it + 1, tn, cn);
           asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
           asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncwarp();
-        const int t = it / nc0, c0 = (it - t * nc0) << 5;
         const uint32_t ld_base = tile + (uint32_t)(it & 1) * QG_TILE + ld_off;
         const int myslot = t * 32 + lane;
         const bool sv = myslot < nslots;
@@ -691,6 +783,7 @@ query_and_group_kernel(const QgParams P) {
           }
         }
         __syncwarp();  // the buffer is free for the loads of step it + 2
+        t = tn; c0 = cn;
       }
     }
   }
@@ -799,10 +892,37 @@ static int prepare(const float *xyz, int B, int N, float radius, bool use_grid, 
   }
   if (feat_t_bytes) g->feat_t = reinterpret_cast<float *>(p);
   if (use_grid) {
-    RFD_CHECK_CUDA(cudaFuncSetAttribute(grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRID_NC * 4),
-                   "grid_build attr");
-    grid_build_kernel<<<dim3(GB_CS, B), GB_THREADS, GRID_NC * 4, st>>>(xyz, N, radius, g->gs, w.count, g->start,
-                                                                       g->sorted);
+    // 16-CTA clusters (non-portable size) halve the per-thread work; few GPCs can host one, so they are used only when
+    // every scene's cluster is co-resident, else the portable 8-CTA form runs
+    static std::atomic<int> max16{-1};
+    auto launch = [&](auto kern, int cs, bool probe, int *nclusters) -> int {
+      RFD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GRID_NC * 4), "grid_build attr");
+      if (cs > 8) RFD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "grid_build attr");
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cs, B);
+      cfg.blockDim = dim3(GB_THREADS);
+      cfg.dynamicSmemBytes = GRID_NC * 4;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (probe) {
+        if (cudaOccupancyMaxActiveClusters(nclusters, kern, &cfg) != cudaSuccess) { (void)cudaGetLastError(); *nclusters = 0; }
+        return RFD_OK;
+      }
+      RFD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, radius, g->gs, w.count, g->start, g->sorted), "grid_build launch");
+      return RFD_OK;
+    };
+    int m16 = max16.load(std::memory_order_relaxed);
+    if (m16 < 0) {
+      const int rc2 = launch(grid_build_kernel<16>, 16, true, &m16);
+      if (rc2 != RFD_OK) return rc2;
+      max16.store(m16, std::memory_order_relaxed);
+    }
+    const int rc3 = (B <= m16) ? launch(grid_build_kernel<16>, 16, false, nullptr) : launch(grid_build_kernel<8>, 8, false, nullptr);
+    if (rc3 != RFD_OK) return rc3;
     RFD_CHECK_LAUNCH("grid_build_kernel");
   }
   return RFD_OK;
@@ -871,7 +991,21 @@ extern "C" int rfd_query_and_group(const float *xyz, const float *new_xyz, const
                  "query_and_group attr");
   const int tasks = h_ceil_div(M, G);
   dim3 grid(h_ceil_div(tasks, BQ_WARPS), B);
-  query_and_group_kernel<<<grid, BQ_THREADS, smem, st>>>(P);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(BQ_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    // only behind a kernel of THIS call (grid build / transposition): they were ordered normally behind everything the
+    // caller enqueued before, so the early start never overtakes a producer of xyz / new_xyz / features
+    cfg.numAttrs = (use_grid || transposed) ? 1 : 0;
+    RFD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, query_and_group_kernel, P), "query_and_group launch");
+  }
   RFD_CHECK_LAUNCH("query_and_group_kernel");
   return RFD_OK;
 }
