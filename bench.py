@@ -233,20 +233,28 @@ def run_gpu(args, rank, world, local):
     clocks = sampler.stop() if rank == 0 else None
     ms_max = D.max_over_ranks(ms, dev)
 
-    # ---- timed region 2: end to end through the public API with host buffers
-    for i in range(3):
-        net.run_host(*host_sets[i & 1], logits_host, dev)
-    torch.cuda.synchronize()
-    D.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    h2d = d2h = 0
-    for i in range(args.steps):
-        h2d, d2h = net.run_host(*host_sets[i & 1], logits_host, dev)
-        torch.cuda.synchronize()  # the step's result is on the host before the next step starts
-    t_e2e = time.perf_counter() - t0
-    D.barrier()
-    t_e2e = D.max_over_ranks(t_e2e, dev)
+    # ---- timed region 2: end to end through the public API with host buffers.  The step's result is what
+    # Generator3D returns to its caller -- the meshes (generator.py:145-168), extracted on the device -- plus the proposal
+    # scores; the variant that ships every logit to the host (round 1's e2e) is timed as well.
+    def e2e_run(result):
+        for i in range(3):
+            net.run_host(*host_sets[i & 1], logits_host, dev, result=result)
+        torch.cuda.synchronize()
+        D.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        for i in range(args.steps):
+            h2d, d2h = net.run_host(*host_sets[i & 1], logits_host, dev, result=result)
+            torch.cuda.synchronize()  # the step's result is on the host before the next step starts
+        t = time.perf_counter() - t0
+        D.barrier()
+        return D.max_over_ranks(t, dev), h2d, d2h
+
+    t_e2e, h2d, d2h = e2e_run("mesh")
+    mesh_stats = {"vertices_per_step": int(net.last_meshes[0].shape[0]), "triangles_per_step": int(net.last_meshes[1].shape[0])}
+    t_e2e_lg, h2d_lg, d2h_lg = e2e_run("logits")
+    t_e2e_b, h2d_b, d2h_b = e2e_run("bits")
 
     # ---- BASELINE config 5: training step with the NCCL gradient all-reduce (every rank takes part)
     train = None
@@ -319,7 +327,15 @@ def run_gpu(args, rank, world, local):
         "fps": {"ms_per_step": sum(fps) / args.steps if fps else None, "launches_per_step": len(fps) // args.steps},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": t_e2e / args.steps * 1e3},
+                "ms_per_step": t_e2e / args.steps * 1e3,
+                "result": "meshes (marching cubes on the device, rfd_extract_mesh: f32 vertices + i32 triangles + "
+                          "per-object ranges) + objectness scores", **mesh_stats},
+        "e2e_all_logits": {"value": world * S * args.steps / t_e2e_lg, "unit": "scenes/s", "h2d_bytes_per_step": h2d_lg,
+                           "d2h_bytes_per_step": d2h_lg, "ms_per_step": t_e2e_lg / args.steps * 1e3,
+                           "result": "every logit (S*256 x 32^3 f32) + objectness scores"},
+        "e2e_occupancy_bits": {"value": world * S * args.steps / t_e2e_b, "unit": "scenes/s", "h2d_bytes_per_step": h2d_b,
+                               "d2h_bytes_per_step": d2h_b, "ms_per_step": t_e2e_b / args.steps * 1e3,
+                               "result": "occupancy bit masks (1 bit per lattice point) + objectness scores"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "train": train,

@@ -168,6 +168,23 @@ int rfd_make_3d_grid(int R, float box_size, float *out, void *stream);
  * external/common.py:7-35 compute_iou), counts (B) i32 = occupied points per object (NULL = skip). */
 int rfd_occupancy_bits(const float *logits, int B, int T, float threshold, uint32_t *bits, int *counts, void *stream);
 
+/* ---- surface extraction: Generator3D.extract_mesh (models/iscnet/modules/generator.py:145-168) for a
+ * batch of objects, on the device: np.pad(occ_hat, 1, -1e6) + mcubes.marching_cubes(., threshold) (PyMCubes 0.1.2,
+ * environment.yml:77; Bourke's table, corner bit set iff value <= threshold) + the vertex transform
+ * box_size * (((v - 0.5) - 1) / (R-1) - 0.5), all evaluated in fp64 in the reference's operation order.
+ *   logits (B, R^3) f32 (x slowest, z fastest: values.reshape(R,R,R), generator.py:97); R <= 32
+ *   threshold = log(t) - log(1-t) as the reference computes it (0.0 for t = 0.5); box_size = 1 + padding
+ *   vertices: pool of cap_vertices x 3 f64 (vertex_f64 != 0) or f32; triangles: pool of cap_triangles x 3 i32 holding
+ *   OBJECT-LOCAL vertex ids; ranges (B,4) i32 = {vertex offset, vertex count, triangle offset, triangle count} of every
+ *   object inside the pools (offsets -1 if the object did not fit: counts are still valid, re-run with larger pools);
+ *   totals: 3 x u64, ZEROED BY THE CALLER, incremented atomically: vertices reserved, triangles reserved, objects that
+ *   did not fit.
+ * Order inside an object: vertices by (lower end point of their lattice edge, axis), triangles by cell (x slowest)
+ * then table order (= PyMCubes' triangle order; its vertex order, which is creation order, is not reproduced). */
+int rfd_extract_mesh(const float *logits, int B, int R, double threshold, double box_size, void *vertices,
+                     int vertex_f64, int *triangles, long long cap_vertices, long long cap_triangles, int *ranges,
+                     unsigned long long *totals, void *stream);
+
 /* ---- (a12) ONet decoder (DecoderCBatchNorm, eval mode), hidden = 256, n_blocks = 5.
  * Step 1 (once per checkpoint): pack the fp32 fc weights into the device layout the kernel streams:
  *   fc_w (10,256,256) f32 = [blocks.0.fc_0, blocks.0.fc_1, blocks.1.fc_0, ...].weight  ([out][in])

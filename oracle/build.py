@@ -4,15 +4,17 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "pointnet2_oracle.c")
+SRCS = [SRC, os.path.join(HERE, "mc_oracle.c")]
+DEPS = SRCS + [os.path.join(HERE, "mc_tables_oracle.h")]
 LIB = os.path.join(HERE, "liboracle.so")
 
 
 def build(force=False):
     if (not force and os.path.exists(LIB)
-            and os.path.getmtime(LIB) >= os.path.getmtime(SRC)):
+            and os.path.getmtime(LIB) >= max(os.path.getmtime(f) for f in DEPS)):
         return LIB
     cmd = ["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "-fPIC",
-           "-o", LIB, SRC, "-lm"]
+           "-o", LIB] + SRCS + ["-lm"]
     subprocess.run(cmd, check=True)
     return LIB
 

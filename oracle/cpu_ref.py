@@ -151,3 +151,47 @@ def query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz=True, norma
     else:
         new_features = grouped_xyz
     return new_features, grouped_xyz, idx
+
+
+def marching_cubes(vol, iso):
+    """mcubes.marching_cubes(vol, iso) restated (oracle/mc_oracle.c): vol (nx,ny,nz) -> vertices (V,3) f64 in lattice
+    index coordinates, triangles (T,3) i32 into them, keys (V,) i32 = 3 * owner lattice point + axis of each vertex's edge."""
+    v = np.ascontiguousarray(vol, dtype=np.float64)
+    nx, ny, nz = v.shape
+    cap_v, cap_t = 3 * v.size + 8, 5 * v.size + 8
+    verts = np.zeros((cap_v, 3), np.float64)
+    keys = np.zeros(cap_v, np.int32)
+    tris = np.zeros((cap_t, 3), np.int32)
+    nv, nt = ctypes.c_int(0), ctypes.c_int(0)
+    lib = _load()
+    lib.oracle_marching_cubes.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_void_p]
+    rc = lib.oracle_marching_cubes(v.ctypes.data_as(ctypes.c_void_p), nx, ny, nz, float(iso),
+                                   verts.ctypes.data_as(ctypes.c_void_p), keys.ctypes.data_as(ctypes.c_void_p), cap_v,
+                                   tris.ctypes.data_as(ctypes.c_void_p), cap_t, ctypes.byref(nv), ctypes.byref(nt))
+    assert rc == 0
+    return verts[:nv.value].copy(), tris[:nt.value].copy(), keys[:nv.value].copy()
+
+
+def extract_mesh(occ_hat, threshold=0.5, padding=0.1):
+    """Generator3D.extract_mesh (generator.py:145-168) up to the trimesh construction: occ_hat (n,n,n) logits ->
+    vertices (V,3) f64 in the object's box frame, triangles (T,3), keys (V,) (see marching_cubes; padded lattice)."""
+    occ_hat = np.asarray(occ_hat)
+    n_x, n_y, n_z = occ_hat.shape
+    box_size = 1 + padding
+    thr = np.log(threshold) - np.log(1. - threshold)
+    occ_hat_padded = np.pad(occ_hat, 1, 'constant', constant_values=-1e6)
+    vertices, triangles, keys = marching_cubes(occ_hat_padded, thr)
+    vertices -= 0.5
+    vertices -= 1
+    vertices /= np.array([n_x - 1, n_y - 1, n_z - 1])
+    vertices = box_size * (vertices - 0.5)
+    return vertices, triangles, keys
+
+
+def mc_table():
+    lib = _load()
+    lib.oracle_mc_table.restype = ctypes.POINTER(ctypes.c_byte)
+    p = lib.oracle_mc_table()
+    return np.ctypeslib.as_array(p, shape=(256, 16)).astype(np.int8).copy()

@@ -34,6 +34,7 @@ SIGNATURES = {
     "rfd_pointwise_mlp_f32": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "rfd_make_3d_grid": [_i, _f, _vp, _vp],
     "rfd_occupancy_bits": [_vp, _i, _i, _f, _vp, _vp, _vp],
+    "rfd_extract_mesh": [_vp, _i, _i, ctypes.c_double, ctypes.c_double, _vp, _i, _vp, _ll, _ll, _vp, _vp, _vp],
     "rfd_mlp_chain_packed_bytes": [_i, _i, _i, _i, _i, _i],
     "rfd_mlp_chain_pack": [_i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp],
     "rfd_mlp_chain": [_i, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],

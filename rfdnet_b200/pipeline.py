@@ -9,7 +9,7 @@ path; callers pass it in (the benchmark uses seeded N(0,1
 import torch
 import torch.nn as nn
 
-from . import detection, onet
+from . import detection, generator, onet
 
 
 class SceneHotPath(nn.Module):
@@ -49,11 +49,18 @@ class SceneHotPath(nn.Module):
         return end_points, logits
 
     @torch.no_grad()
-    def run_host(self, pc_host, codes_host, logits_host, device, chunks=4):
-        """End-to-end call with HOST (pinned) buffers: H2D of the clouds and shape codes, the pass, D2H of ALL logits
-        and of the proposal scores.  The decoder runs in `chunks` object chunks; the D2H copy of a finished chunk
-        overlaps the decoding of the next one on a second stream.  Returns bytes moved (h2d, d2h); the caller
-        synchronises the device (both streams are joined before returning control of the buffers)."""
+    def run_host(self, pc_host, codes_host, logits_host, device, chunks=4, result="logits", mesh_capacity=(24576, 49152)):
+        """End-to-end call with HOST (pinned) buffers: H2D of the clouds and shape codes, the pass, D2H of the result and
+        of the proposal scores.  The decoder runs in `chunks` object chunks.
+          result="logits": ALL logits come back (logits_host (B*K, R^3) pinned); the D2H of a finished chunk overlaps the
+                           decoding of the next one on a second stream.
+          result="mesh":   what Generator3D hands to its caller (generator.py:145-168): every chunk's logits go through
+                           rfd_extract_mesh on the device into shared vertex / triangle pools; only the used part of the
+                           pools is copied, chunk by chunk, under the decoding of the following chunks.
+                           `mesh_capacity` = (vertices, triangles) reserved per object in the device pools.  The meshes
+                           are left in self.last_meshes = (vertices, triangles, ranges) numpy views of pinned buffers.
+          result="bits":   occupancy masks only (rfd_occupancy_bits, 1 bit per lattice point) in self.last_bits.
+        Returns bytes moved (h2d, d2h); the caller synchronises the device."""
         main = torch.cuda.current_stream(device)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device)
@@ -66,6 +73,21 @@ class SceneHotPath(nn.Module):
         grid = self.grid(device)
         z = torch.zeros((nobj, self.z_dim), dtype=torch.float32, device=device)
         step = (nobj + chunks - 1) // chunks
+        h2d = pc_host.numel() * 4 + codes_host.numel() * 4
+        if result == "mesh":
+            return h2d, self._run_mesh_result(main, copy, grid, z, codes, nobj, step, mesh_capacity, device) + scores.numel() * 4
+        if result == "bits":
+            # occupancy only (voxel IoU, external/common.py:7-35): 1 bit per lattice point instead of 32
+            words = (self.resolution ** 3 + 31) // 32
+            if getattr(self, "_bits_host", None) is None or self._bits_host.shape != (nobj, words):
+                self._bits_host = torch.empty((nobj, words), dtype=torch.int32).pin_memory()
+            for lo in range(0, nobj, step):
+                hi = min(nobj, lo + step)
+                lg = self.decoder.decode(grid, z[lo:hi], codes[lo:hi].contiguous())
+                bits, _ = onet.occupancy_bits(lg, 0.0)
+                self._bits_host[lo:hi].copy_(bits, non_blocking=True)
+            self.last_bits = self._bits_host
+            return h2d, nobj * words * 4 + scores.numel() * 4
         keep = []
         for lo in range(0, nobj, step):
             hi = min(nobj, lo + step)
@@ -78,6 +100,65 @@ class SceneHotPath(nn.Module):
             lg.record_stream(copy)
             keep.append(lg)
         main.wait_stream(copy)
-        h2d = pc_host.numel() * 4 + codes_host.numel() * 4
         d2h = logits_host.numel() * 4 + scores.numel() * 4
         return h2d, d2h
+
+    def _run_mesh_result(self, main, copy, grid, z, codes, nobj, step, capacity, device):
+        """decode + rfd_extract_mesh per object chunk into shared pools; the kernels of a chunk run back to back on the
+        main stream, so chunk i owns the pool range between the fill levels after chunks i-1 and i.  The host learns a
+        chunk's fill level from a 24-byte snapshot, then copies exactly that range on the copy stream while the next
+        chunks are still being decoded."""
+        mp = self._mesh_pools(nobj, capacity, device)
+        mp["totals"].zero_()
+        events, bounds = [], []
+        for ci, lo in enumerate(range(0, nobj, step)):
+            hi = min(nobj, lo + step)
+            lg = self.decoder.decode(grid, z[lo:hi], codes[lo:hi].contiguous())
+            generator.extract_meshes(lg, self.resolution, 0.5, self.box_size - 1.0, pools=(mp["v"], mp["t"]),
+                                     ranges=mp["ranges"][lo:hi], totals=mp["totals"])
+            mp["h_snap"][ci].copy_(mp["totals"], non_blocking=True)
+            mp["h_ranges"][lo:hi].copy_(mp["ranges"][lo:hi], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            events.append(ev)
+            bounds.append((lo, hi))
+        pv = pt = 0
+        grow = False
+        for ci, ev in enumerate(events):
+            ev.synchronize()
+            nv, nt, nofit = (int(x) for x in mp["h_snap"][ci])
+            if nofit:
+                raise RuntimeError(f"run_host: {nofit} object(s) did not fit in the mesh pools ({nv} vertices / {nt} "
+                                   f"triangles reserved so far for {nobj} objects); raise mesh_capacity")
+            grow = grow or nv > mp["h_v"].shape[0] or nt > mp["h_t"].shape[0]
+            if not grow:
+                with torch.cuda.stream(copy):
+                    mp["h_v"][pv:nv].copy_(mp["v"][pv:nv], non_blocking=True)
+                    mp["h_t"][pt:nt].copy_(mp["t"][pt:nt], non_blocking=True)
+            pv, pt = nv, nt
+        if grow:   # pinned host pools too small (first steps): regrow with headroom, copy everything once
+            copy.synchronize()
+            mp["h_v"] = torch.empty((pv + pv // 2, 3), dtype=torch.float32).pin_memory()
+            mp["h_t"] = torch.empty((pt + pt // 2, 3), dtype=torch.int32).pin_memory()
+            mp["h_v"][:pv].copy_(mp["v"][:pv], non_blocking=True)
+            mp["h_t"][:pt].copy_(mp["t"][:pt], non_blocking=True)
+        main.wait_stream(copy)
+        self.last_meshes = (mp["h_v"][:pv].numpy(), mp["h_t"][:pt].numpy(), mp["h_ranges"][:nobj].numpy())
+        return pv * 12 + pt * 12 + nobj * 16 + 24 * len(events)
+
+    def _mesh_pools(self, nobj, capacity, device):
+        key = (nobj, tuple(capacity), str(device))
+        mp = getattr(self, "_mesh_pool_cache", None)
+        if mp is None or mp["key"] != key:
+            cv, ct = nobj * capacity[0], nobj * capacity[1]
+            mp = {"key": key,
+                  "v": torch.empty((cv, 3), dtype=torch.float32, device=device),
+                  "t": torch.empty((ct, 3), dtype=torch.int32, device=device),
+                  "ranges": torch.empty((nobj, 4), dtype=torch.int32, device=device),
+                  "totals": torch.zeros((3,), dtype=torch.int64, device=device),
+                  "h_v": torch.empty((0, 3), dtype=torch.float32),
+                  "h_t": torch.empty((0, 3), dtype=torch.int32),
+                  "h_ranges": torch.empty((nobj, 4), dtype=torch.int32).pin_memory(),
+                  "h_snap": torch.empty((64, 3), dtype=torch.int64).pin_memory()}
+            self._mesh_pool_cache = mp
+        return mp
