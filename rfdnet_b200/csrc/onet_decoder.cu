@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1)
 onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const float *__restrict__ fc_p_w,
                    const uint8_t *__restrict__ packed, const float *__restrict__ aff_all,
                    const float *__restrict__ fc_out_w, float fc_out_b, float *__restrict__ logits, int num_tiles,
-                   int tiles_per_obj, unsigned long long *__restrict__ trace) {
+                   int tiles_per_obj, unsigned long long *__restrict__ trace, int fuse_e0) {
   constexpr int NSTAGE = MODE == MODE_F16X3 ? 2 : 4;
   constexpr int SPK = MODE == MODE_F16X3 ? 2 : 1;  // weight stages per (layer, k-panel): hi [, lo]
   constexpr int SM_W = MODE == MODE_F16X3 ? 2 * DEC_KP * DEC_PANEL_A : DEC_KP * DEC_PANEL_A;
@@ -256,74 +256,95 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint32_t layer_count = 0;
     int cur_obj = -1;
+    bool e0_done = false;  // the E0 step of this slot's tile already ran inside the previous tile's final epilogue
+    // shared-space byte addresses (explicit ld.shared / st.shared: the compiler otherwise emits generic LD/ST)
+    const uint32_t aff_a = umma::smem_u32(s_aff);  // [x_bias 256][11][128 pairs]{a0,a1,c0,c1}
+    const uint32_t affi_a = aff_a + DEC_H * 4 + lc * 16;                  // + layer*2048 + (col/2)*16
+    const uint32_t pan0 = umma::smem_u32(s_ah) + (q * 32 + lr) * 128 + lc * 4;  // + kp*PANEL + j*1024 + swizzled chunk
+    const uint32_t wp_a = umma::smem_u32(s_wp), wout_a = umma::smem_u32(s_wout);
+    // query points of a tile: row j of this thread is point t0 + 8j of the tile's object
+    auto load_p = [&](int tile, float (&px)[4], float (&py)[4], float (&pz)[4]) {
+      const int obj = tile / tiles_per_obj;
+      const int t0 = (tile - obj * tiles_per_obj) * DEC_TILE_M + q * 32 + lr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int t = t0 + 8 * j;
+        px[j] = py[j] = pz[j] = 0.f;
+        if (t < T) {
+          const float *pp = p + (size_t)obj * p_stride + (size_t)t * 3;
+          px[j] = __ldg(pp); py[j] = __ldg(pp + 1); pz[j] = __ldg(pp + 2);
+        }
+      }
+    };
+    // E0 of one 64-column panel: x0 = fc_p(p) + (fc_p.bias + fc_z(z)) in fp32 -> TMEM ; h0 = relu(a0*x0 + c0) -> A panel kp
+    auto e0_panel = [&](int kp, const float (&px)[4], const float (&py)[4], const float (&pz)[4]) {
+      const int cb = kp * 64 + cq * DEC_CW;
+      uint32_t v[2][8];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int col = cb + 8 * i + 2 * lc;
+        const float2 w0 = umma::lds_f2(wp_a + col * 4);
+        const float2 w1 = umma::lds_f2(wp_a + (DEC_H + col) * 4);
+        const float2 w2 = umma::lds_f2(wp_a + (2 * DEC_H + col) * 4);
+        const float2 xb = umma::lds_f2(aff_a + col * 4);
+        const float4 ac = umma::lds_f4(affi_a + (cb >> 1) * 16 + i * 64);
+        const uint32_t sw = (uint32_t)(((cq * 2 + i) ^ lr) << 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float x0 = fmaf(px[j], w0.x, xb.x), x1 = fmaf(px[j], w0.y, xb.y);
+          x0 = fmaf(py[j], w1.x, x0); x1 = fmaf(py[j], w1.y, x1);
+          x0 = fmaf(pz[j], w2.x, x0); x1 = fmaf(pz[j], w2.y, x1);
+          v[j >> 1][4 * i + 2 * (j & 1)] = __float_as_uint(x0);
+          v[j >> 1][4 * i + 2 * (j & 1) + 1] = __float_as_uint(x1);
+          store_act_pair<MODE>(pan0 + kp * DEC_PANEL_A + j * 1024 + sw, fmaf(x0, ac.x, ac.z), fmaf(x1, ac.y, ac.w));
+        }
+      }
+      umma::tmem_st_16x256b_x2(tmem_x + lane_base + cb, v[0]);
+      umma::tmem_st_16x256b_x2(tmem_x + lane_base + (16u << 16) + cb, v[1]);
+      umma::tc_wait_st();
+      umma::fence_proxy_async_smem();
+      umma::tc_fence_before();
+      asm volatile("bar.arrive %0, %1;" ::"r"(2 + kp), "n"(32 * DEC_EPI_WARPS + 32) : "memory");
+    };
     for (int slot = 0; slot < n_slots; ++slot) {
       const int tile = tile0 + slot * CL;
       if (tile >= c_hi) break;
       const int obj = tile / tiles_per_obj;
       const int t0 = (tile - obj * tiles_per_obj) * DEC_TILE_M + q * 32 + lr;  // row j of this thread: t0 + 8j
-      if (obj != cur_obj) {
-        // (re)load this object's x_bias + paired (a,c) table: 5888 floats, all 16 epilogue warps cooperate
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * DEC_EPI_WARPS) : "memory");  // everyone is done with the old table
-        const float4 *src4 = reinterpret_cast<const float4 *>(aff_all + (size_t)obj * DEC_REC_FLOATS + DEC_PLAIN_FLOATS);
-        float4 *dst4 = reinterpret_cast<float4 *>(s_aff);
-        for (int e = tid - 64; e < DEC_AFF_FLOATS / 4; e += 32 * DEC_EPI_WARPS) dst4[e] = __ldg(src4 + e);
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * DEC_EPI_WARPS) : "memory");
-        cur_obj = obj;
-      }
-      // shared-space byte addresses (explicit ld.shared / st.shared: the compiler otherwise emits generic LD/ST)
-      const uint32_t aff_a = umma::smem_u32(s_aff);  // [x_bias 256][11][128 pairs]{a0,a1,c0,c1}
-      const uint32_t affi_a = aff_a + DEC_H * 4 + lc * 16;                  // + layer*2048 + (col/2)*16
-      const uint32_t pan0 = umma::smem_u32(s_ah) + (q * 32 + lr) * 128 + lc * 4;  // + kp*PANEL + j*1024 + swizzled chunk
-      const uint32_t wp_a = umma::smem_u32(s_wp), wout_a = umma::smem_u32(s_wout);
-      // ---- E0: x0 = fc_p(p) + (fc_p.bias + fc_z(z)) in fp32 -> TMEM ; h0 = relu(a0*x0 + c0) -> A panels
-      {
+      if (!e0_done) {
+        if (obj != cur_obj) {
+          // (re)load this object's x_bias + paired (a,c) table: 5888 floats, all 16 epilogue warps cooperate
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * DEC_EPI_WARPS) : "memory");  // everyone is done with the old table
+          const float4 *src4 = reinterpret_cast<const float4 *>(aff_all + (size_t)obj * DEC_REC_FLOATS + DEC_PLAIN_FLOATS);
+          float4 *dst4 = reinterpret_cast<float4 *>(s_aff);
+          for (int e = tid - 64; e < DEC_AFF_FLOATS / 4; e += 32 * DEC_EPI_WARPS) dst4[e] = __ldg(src4 + e);
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * DEC_EPI_WARPS) : "memory");
+          cur_obj = obj;
+        }
         float px[4], py[4], pz[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int t = t0 + 8 * j;
-          px[j] = py[j] = pz[j] = 0.f;
-          if (t < T) {
-            const float *pp = p + (size_t)obj * p_stride + (size_t)t * 3;
-            px[j] = __ldg(pp); py[j] = __ldg(pp + 1); pz[j] = __ldg(pp + 2);
-          }
-        }
+        load_p(tile, px, py, pz);
 #pragma unroll 1
-        for (int kp = 0; kp < DEC_KP; ++kp) {
-          const int cb = kp * 64 + cq * DEC_CW;
-          uint32_t v[2][8];
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int col = cb + 8 * i + 2 * lc;
-            const float2 w0 = umma::lds_f2(wp_a + col * 4);
-            const float2 w1 = umma::lds_f2(wp_a + (DEC_H + col) * 4);
-            const float2 w2 = umma::lds_f2(wp_a + (2 * DEC_H + col) * 4);
-            const float2 xb = umma::lds_f2(aff_a + col * 4);
-            const float4 ac = umma::lds_f4(affi_a + (cb >> 1) * 16 + i * 64);
-            const uint32_t sw = (uint32_t)(((cq * 2 + i) ^ lr) << 4);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float x0 = fmaf(px[j], w0.x, xb.x), x1 = fmaf(px[j], w0.y, xb.y);
-              x0 = fmaf(py[j], w1.x, x0); x1 = fmaf(py[j], w1.y, x1);
-              x0 = fmaf(pz[j], w2.x, x0); x1 = fmaf(pz[j], w2.y, x1);
-              v[j >> 1][4 * i + 2 * (j & 1)] = __float_as_uint(x0);
-              v[j >> 1][4 * i + 2 * (j & 1) + 1] = __float_as_uint(x1);
-              store_act_pair<MODE>(pan0 + kp * DEC_PANEL_A + j * 1024 + sw, fmaf(x0, ac.x, ac.z), fmaf(x1, ac.y, ac.w));
-            }
-          }
-          umma::tmem_st_16x256b_x2(tmem_x + lane_base + cb, v[0]);
-          umma::tmem_st_16x256b_x2(tmem_x + lane_base + (16u << 16) + cb, v[1]);
-          umma::tc_wait_st();
-          umma::fence_proxy_async_smem();
-          umma::tc_fence_before();
-          asm volatile("bar.arrive %0, %1;" ::"r"(2 + kp), "n"(32 * DEC_EPI_WARPS + 32) : "memory");
-        }
+        for (int kp = 0; kp < DEC_KP; ++kp) e0_panel(kp, px, py, pz);
       }
+      e0_done = false;
       // ---- layers
 #pragma unroll 1
       for (int l = 0; l < DEC_LAYERS; ++l, ++layer_count) {
         // (a,c) of this warp's first panel are fetched while the MMAs of the layer are still running
         const float4 pre0 = umma::lds_f4(affi_a + (l + 1) * (DEC_H * 2 * 4) + cq * (DEC_CW / 2) * 16);
         const float4 pre1 = umma::lds_f4(affi_a + (l + 1) * (DEC_H * 2 * 4) + cq * (DEC_CW / 2) * 16 + 64);
+        // last layer: the NEXT tile's query points are fetched now, and -- when it belongs to the same object (same
+        // affine table) -- its E0 step is interleaved panel by panel with this tile's fc_out below, so the tensor pipe
+        // restarts after one panel instead of after the whole tile boundary (final epilogue + point loads + E0)
+        float npx[4], npy[4], npz[4];
+        bool fuse = false;
+        if (l == DEC_LAYERS - 1) {
+          const int ntile = tile + CL;
+          if (fuse_e0 && slot + 1 < n_slots && ntile < c_hi && ntile / tiles_per_obj == obj) {
+            fuse = true;
+            load_p(ntile, npx, npy, npz);
+          }
+        }
         umma::mbar_wait(&bars->acc_ready, layer_count & 1u);
         umma::tc_fence_after();
         const bool tr = TRACE && blockIdx.x == 0 && slot < 2 && warp == 2 && lane == 0;
@@ -369,7 +390,7 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
           float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int kp = 0; kp < DEC_KP; ++kp) {
-            const float4 acs[2] = {umma::lds_f4(al + kp * 512), umma::lds_f4(al + kp * 512 + 64)};
+            const float4 acs[2] = {kp ? umma::lds_f4(al + kp * 512) : pre0, kp ? umma::lds_f4(al + kp * 512 + 64) : pre1};
             const float2 wos[2] = {umma::lds_f2(wout_a + (kp * 64 + cq * DEC_CW + 2 * lc) * 4),
                                    umma::lds_f2(wout_a + (kp * 64 + cq * DEC_CW + 8 + 2 * lc) * 4)};
             umma::tc_wait_ld();
@@ -386,6 +407,12 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
                 part[j] = fmaf(fmaxf(fmaf(x0, acs[i].x, acs[i].z), 0.f), wos[i].x, part[j]);
                 part[j] = fmaf(fmaxf(fmaf(x1, acs[i].y, acs[i].w), 0.f), wos[i].y, part[j]);
               }
+            }
+            if (fuse) {
+              // this warp has read its (rows, columns) block of panel kp of x -- the only reader of that block -- and the
+              // MMAs of this tile are complete (acc_ready): the block of the next tile's x0 and A panel can take its place
+              // (the 64 FMAs above first: they free the panel's registers before E0 needs its own)
+              e0_panel(kp, npx, npy, npz);
             }
           }
 #pragma unroll
@@ -405,6 +432,7 @@ onet_decode_kernel(const float *__restrict__ p, long long p_stride, int T, const
                     ((s_out[rr] + s_out[DEC_TILE_M + rr]) + (s_out[2 * DEC_TILE_M + rr] + s_out[3 * DEC_TILE_M + rr])) + fc_out_b;
             }
           }
+          e0_done = fuse;
         }
       }
     }
@@ -757,8 +785,9 @@ static int launch_decode_t(const float *p, long long p_stride, int T, const floa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  static const int fuse_e0 = [] { const char *e = getenv("RFD_ONET_FUSE_E0"); return (e && e[0] == '0') ? 0 : 1; }();
   RFD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p, p_stride, T, fc_p_w, packed, aff, fc_out_w, fc_out_b, logits, num_tiles,
-                                    tiles_per_obj, trace),
+                                    tiles_per_obj, trace, fuse_e0),
                  "onet_decode_kernel launch");
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return RFD_OK;

@@ -91,7 +91,7 @@ def test_default_mode_is_fp16():
     assert onet.DecoderCBatchNorm(dim=3, z_dim=32, c_dim=512).precision == "fp16"
 
 
-@pytest.mark.parametrize("B,T", [(1, 1), (2, 127), (3, 129), (5, 1000), (300, 256), (1, 128), (1, 129)])
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 127), (3, 129), (5, 1000), (300, 256), (1, 128), (1, 129), (700, 300)])
 @pytest.mark.parametrize("cluster", [1, 2])
 def test_decoder_modes_vs_fp32_ragged_sizes(B, T, cluster):
     """ragged tile counts: odd numbers of 128-point tiles exercise the phantom pass of the weight-sharing CTA pairs."""

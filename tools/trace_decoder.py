@@ -22,6 +22,8 @@ print("layer | mma ready kp0..3 | mma issued kp0..3 | epi sees acc | epi publish
 for l in range(10):
     r = tile[l] - base
     print(l, "|", list(r[0:4]), "|", list(r[4:8]), "|", r[8], "|", list(r[9:13]))
+print("tile period (layer-0 mma ready, tile 0 -> tile 1):", int(t[1, 0, 0] - t[0, 0, 0]), " sum of the 9 layer periods of tile 1:",
+      int(tile[9, 0] - tile[0, 0]), " last layer's first mma ready -> next tile's first mma ready (tile 0 -> 1):", int(t[1, 0, 0] - t[0, 9, 0]))
 print("layer period (mma ready kp0 -> next layer's):", [int(tile[l + 1, 0] - tile[l, 0]) for l in range(9)])
 print("gap: last issue of layer l -> first ready of layer l+1:", [int(tile[l + 1, 0] - tile[l, 7]) for l in range(9)])
 print("epilogue: acc seen -> panel0 published:", [int(tile[l, 9] - tile[l, 8]) for l in range(9)])
