@@ -50,7 +50,7 @@ extern "C" {
 #define RFD_ERR_CUDA (-3)             /* a CUDA runtime call or launch failed; see rfd_last_error() */
 #define RFD_ERR_NO_DEVICE (-4)        /* no sm_100 device / wrong architecture */
 
-#define RFD_ABI_VERSION 3
+#define RFD_ABI_VERSION 4
 
 int rfd_abi_version(void);
 const char *rfd_status_string(int status);

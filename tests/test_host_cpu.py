@@ -25,7 +25,7 @@ def test_cabi_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/rfdnet_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.rfd_abi_version() == 3
+    assert lib.rfd_abi_version() == 4
     assert b"invalid" in lib.rfd_status_string(-1)
     # argument validation happens before any CUDA call, so it is testable without a GPU
     assert lib.rfd_furthest_point_sampling(None, 1, 0, 4, None, None) == -1
