@@ -280,6 +280,15 @@ def run_gpu(args, rank, world, local):
     value = world * S * args.steps / (ms_max * 1e-3)
     e2e = world * S * args.steps / t_e2e
     qg = ballquery_group_bench(net, dev_sets[0][0], hbm)
+    skip = None
+    try:
+        with torch.no_grad():
+            ep0, _ = net.detection(dev_sets[0][0][:1].contiguous())
+        skip = skip_propagation_bench(dev, dev_sets[0][0], ep0)
+    except Exception as e:  # an (f)-row extra must never take the headline line down
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        skip = {"error": repr(e)[:300]}
 
     # ---- CPU baseline (bounded sample, rank 0, N = 1 only)
     cpu = None
@@ -339,6 +348,7 @@ def run_gpu(args, rank, world, local):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "train": train,
+        "skip_propagation": skip,
     }
     print(json.dumps(line))
 
@@ -411,6 +421,45 @@ def train_bench(args, rank, world, dev):
            "loss_first_last": [losses[0], losses[-1]], "loss_finite": bool(finite),
            "collective": "nccl all_reduce(AVG) per bucket, async from post-accumulate-grad hooks" if world > 1 else "none (1 GPU)"}
     del trainer, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def skip_propagation_bench(dev, pc, ep):
+    """SkipPropagation.generate for the 256 proposals of ONE 80k-point scene -- STN_Group (ball query
+    r = 1.0 / nsample = 1024 + heading rotation + STN3d alignment) on this library's kernels (4 launches), PointSeg and
+    ResnetPointnet (hidden 512) on PyTorch's library GEMMs -- producing the 512-d shape codes the decoder consumes."""
+    from rfdnet_b200 import completion
+    from rfdnet_b200.synth import seeded_fill
+    sp = completion.SkipPropagation(input_feature_dim=1, c_dim=512, hidden_dim=512).eval()
+    seeded_fill(sp, 17)
+    sp = sp.to(dev)
+    pc1 = pc[:1].contiguous()
+    box_xyz = ep["center"][:1].contiguous()
+    heading = torch.argmax(ep["heading_scores"][:1], -1).float() * (2 * np.pi / 12)
+    box_feat = torch.randn(1, 128, 256, device=dev)
+    xyz = pc1[..., :3].contiguous()
+    feats = torch.cat([pc1[..., 3:].transpose(1, 2), torch.zeros(1, 1, pc1.shape[1], device=dev)], 1).contiguous()
+
+    def timed(fn, n=3):
+        with torch.no_grad():
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, out
+
+    stn_ms, _ = timed(lambda: sp.stn(xyz, feats, box_xyz, heading))
+    tot_ms, codes = timed(lambda: sp.generate(box_xyz, heading, box_feat, pc1), n=2)
+    out = {"proposals": 256, "points": int(pc1.shape[1]), "nsample": 1024, "stn_group_ms": stn_ms, "generate_ms": tot_ms,
+           "codes_shape": list(codes.shape), "codes_finite": bool(torch.isfinite(codes).all()),
+           "note": "stn_group_ms: rfd_query_and_group_rotated + 2 x rfd_mlp_chain (tcgen05, x3) + rfd_stn_apply; the rest of "
+                   "generate_ms is PointSeg + ResnetPointnet on torch (fp32 library GEMMs)"}
+    del sp
     torch.cuda.empty_cache()
     return out
 

@@ -160,6 +160,17 @@ int rfd_sa_mlp_chain(int mode, const float *xyz, const float *new_xyz, const flo
 /* features (B,C,N) channel-major -> point-major (B,N,Cp), Cp >= C a multiple of 4, padding zero-filled */
 int rfd_transpose_features(const float *features, int B, int C, int N, int Cp, float *out, void *stream);
 
+/* ---- STN_Group (pointnet2_modules.py:468-537), the per-proposal grouping of SkipPropagation.
+ * rfd_query_and_group_rotated = rfd_query_and_group + the rotation of the relative coordinates about z by the box heading
+ * (rot = [[cos, sin, 0], [-sin, cos, 0], [0, 0, 1]], :513-526), heading (B,M) radians, in the same kernel (RfD-Net:
+ * radius 1.0, nsample 1024 over the whole cloud).  rfd_stn_apply = STN3d's last step (:455-462): theta (B,12,M) is the
+ * regressed 3x4 matrix (row major, WITHOUT the identity, which the kernel adds), out = theta[:, :3] . g + theta[:, 3]. */
+int rfd_query_and_group_rotated(const float *xyz, const float *new_xyz, const float *features, const float *heading,
+                                int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz,
+                                float *new_features, float *grouped_xyz, int *idx, void *stream);
+int rfd_stn_apply(const float *grouped_xyz /*(B,3,M,S)*/, const float *theta /*(B,12,M)*/, int B, int M, int S,
+                  float *out /*(B,3,M,S)*/, void *stream);
+
 /* ---- (a13) occupancy query lattice: out (R^3,3) f32 = box_size * linspace(-0.5,0.5,R) on each axis, z fastest */
 int rfd_make_3d_grid(int R, float box_size, float *out, void *stream);
 

@@ -27,6 +27,8 @@ SIGNATURES = {
     "rfd_group_points": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "rfd_group_points_grad": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "rfd_query_and_group": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "rfd_query_and_group_rotated": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "rfd_stn_apply": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "rfd_three_nn": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "rfd_three_interpolate": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "rfd_three_interpolate_grad": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],

@@ -531,6 +531,7 @@ struct QgParams {
   const int *gstart;
   const float4 *gsorted;
   int cloud_pts;                                   // staged points per pass (multiple of 128), 0 in grid mode
+  const float *heading;                            // (B, M) or nullptr: rotate the relative xyz about z by -heading (STN_Group)
 };
 
 constexpr int QG_MAX_G = 4;
@@ -682,6 +683,12 @@ query_and_group_kernel(const QgParams P) {
     // torch lowers `tensor /= python_float` on CUDA to a multiply with the f32 reciprocal (pointnet2_utils.py:337)
     const float inv_r = P.normalize_xyz ? __frcp_rn(P.radius) : 1.0f;
     float *gx = P.grouped_xyz ? P.grouped_xyz + (size_t)b * 3 * MS + slot_base : nullptr;
+    float hc[QG_MAX_G], hs[QG_MAX_G];
+#pragma unroll
+    for (int g = 0; g < QG_MAX_G; ++g) {
+      hc[g] = 1.f; hs[g] = 0.f;
+      if (P.heading && g < nq) { const float h = __ldg(P.heading + (size_t)b * m + j0 + g); hc[g] = cosf(h); hs[g] = sinf(h); }
+    }
     for (int e = lane; e < nslots; e += 32) {
       const int q = P.s_shift >= 0 ? (e >> P.s_shift) : e / S;
       const int k = lds_s32(idx_a + 4u * e);
@@ -699,6 +706,15 @@ query_and_group_kernel(const QgParams P) {
         if (q == g) { cxq = qx[g]; cyq = qy[g]; czq = qz[g]; }
       float v0 = __fsub_rn(px, cxq), v1 = __fsub_rn(py, cyq), v2 = __fsub_rn(pz, czq);  // :335 grouped_xyz -= new_xyz
       if (P.normalize_xyz) { v0 = __fmul_rn(v0, inv_r); v1 = __fmul_rn(v1, inv_r); v2 = __fmul_rn(v2, inv_r); }  // :337
+      if (P.heading) {
+        // STN_Group (pointnet2_modules.py:513-526): rot = [[cos, sin, 0], [-sin, cos, 0], [0, 0, 1]] applied by bmm
+        float rc = hc[0], rs = hs[0];
+#pragma unroll
+        for (int g = 1; g < QG_MAX_G; ++g)
+          if (q == g) { rc = hc[g]; rs = hs[g]; }
+        const float r0 = fmaf(rs, v1, __fmul_rn(rc, v0)), r1 = fmaf(rc, v1, __fmul_rn(-rs, v0));
+        v0 = r0; v1 = r1;
+      }
       if (P.use_xyz) { out[e] = v0; out[MS + e] = v1; out[2 * MS + e] = v2; }
       if (gx) { gx[e] = v0; gx[MS + e] = v1; gx[2 * MS + e] = v2; }
     }
@@ -949,9 +965,9 @@ extern "C" int rfd_ball_query(const float *new_xyz, const float *xyz, int B, int
   return RFD_OK;
 }
 
-extern "C" int rfd_query_and_group(const float *xyz, const float *new_xyz, const float *features, int B, int N, int M,
-                                   int C, float radius, int nsample, int use_xyz, int normalize_xyz,
-                                   float *new_features, float *grouped_xyz, int *idx, void *stream) {
+static int query_and_group_impl(const float *xyz, const float *new_xyz, const float *features, const float *heading, int B,
+                                int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz,
+                                float *new_features, float *grouped_xyz, int *idx, void *stream) {
   if (B < 0 || N < 0 || M < 0 || C < 0 || nsample < 0) return RFD_ERR_INVALID_ARGUMENT;
   if (B == 0 || M == 0 || nsample == 0) return RFD_OK;
   if (!xyz || !new_xyz || (C > 0 && !features) || !new_features) return RFD_ERR_INVALID_ARGUMENT;
@@ -962,14 +978,15 @@ extern "C" int rfd_query_and_group(const float *xyz, const float *new_xyz, const
   P.xyz = xyz; P.new_xyz = new_xyz; P.features = features;
   P.n = N; P.m = M; P.C = C; P.nsample = nsample; P.radius = radius;
   P.use_xyz = use_xyz; P.normalize_xyz = normalize_xyz;
-  P.new_features = new_features; P.grouped_xyz = grouped_xyz; P.idx_out = idx;
+  P.new_features = new_features; P.grouped_xyz = grouped_xyz; P.idx_out = idx; P.heading = heading;
   P.s_shift = (nsample & (nsample - 1)) == 0 ? __builtin_ctz((unsigned)nsample) : -1;
   // queries per warp task: enough to fill a 32-slot tile (nsample < 32), never more than QG_MAX_G
   int G = nsample >= 32 ? 1 : 32 / nsample;
   if (G > QG_MAX_G) G = QG_MAX_G;
   if (G < 1) G = 1;
   P.G = G;
-  const bool use_grid = N >= GRID_MIN_N && radius > 0.f;
+  // (a grid scan keeps at most GRID_CAP hits: wider groups scan the cloud in index order and stop at nsample hits)
+  const bool use_grid = N >= GRID_MIN_N && radius > 0.f && nsample <= GRID_CAP / 2;
   // the point-major copy is worth its pass from 8 channels on; its 32-bit row offsets need N * Cp < 2^32
   const bool transposed = C >= 8 && (unsigned long long)N * (unsigned long long)((C + 3) & ~3) < 0xffffffffull;
   P.Cp = transposed ? (C + 3) & ~3 : 0;
@@ -1007,6 +1024,56 @@ extern "C" int rfd_query_and_group(const float *xyz, const float *new_xyz, const
     RFD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, query_and_group_kernel, P), "query_and_group launch");
   }
   RFD_CHECK_LAUNCH("query_and_group_kernel");
+  return RFD_OK;
+}
+
+extern "C" int rfd_query_and_group(const float *xyz, const float *new_xyz, const float *features, int B, int N, int M,
+                                   int C, float radius, int nsample, int use_xyz, int normalize_xyz,
+                                   float *new_features, float *grouped_xyz, int *idx, void *stream) {
+  return query_and_group_impl(xyz, new_xyz, features, nullptr, B, N, M, C, radius, nsample, use_xyz, normalize_xyz,
+                              new_features, grouped_xyz, idx, stream);
+}
+
+// STN_Group's grouping (pointnet2_modules.py:497-526): QueryAndGroup(ret_grouped_xyz) + the per-proposal rotation of the
+// relative coordinates by the box heading, in the same kernel.  heading (B, M) radians.
+extern "C" int rfd_query_and_group_rotated(const float *xyz, const float *new_xyz, const float *features,
+                                           const float *heading, int B, int N, int M, int C, float radius, int nsample,
+                                           int use_xyz, int normalize_xyz, float *new_features, float *grouped_xyz,
+                                           int *idx, void *stream) {
+  if (!heading && (long long)B * M > 0) return RFD_ERR_INVALID_ARGUMENT;
+  if (!grouped_xyz && !use_xyz && (long long)B * M > 0) return RFD_ERR_INVALID_ARGUMENT;  // nothing would carry the rotation
+  return query_and_group_impl(xyz, new_xyz, features, heading, B, N, M, C, radius, nsample, use_xyz, normalize_xyz,
+                              new_features, grouped_xyz, idx, stream);
+}
+
+// STN3d's final step (pointnet2_modules.py:455-462): out[b,:,m,s] = (theta[b,:,m] + [I | 0]) as a 3x4 matrix applied to
+// g[b,:,m,s];  theta (B,12,M) channel-major (row-major 3x4 entries), g / out (B,3,M,S).  In place allowed.
+__global__ void __launch_bounds__(256)
+stn_apply_kernel(const float *__restrict__ g, const float *__restrict__ theta, int M, int S, float *__restrict__ out) {
+  const int b = blockIdx.z, mq = blockIdx.y;
+  const size_t MS = (size_t)M * S;
+  const float *th = theta + (size_t)b * 12 * M + mq;
+  float t[12];
+#pragma unroll
+  for (int e = 0; e < 12; ++e) t[e] = __ldg(th + (size_t)e * M) + ((e == 0 || e == 5 || e == 10) ? 1.f : 0.f);
+  const float *gb = g + (size_t)b * 3 * MS + (size_t)mq * S;
+  float *ob = out + (size_t)b * 3 * MS + (size_t)mq * S;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+    const float x = gb[s], y = gb[MS + s], z = gb[2 * MS + s];
+    ob[s] = fmaf(t[2], z, fmaf(t[1], y, t[0] * x)) + t[3];
+    ob[MS + s] = fmaf(t[6], z, fmaf(t[5], y, t[4] * x)) + t[7];
+    ob[2 * MS + s] = fmaf(t[10], z, fmaf(t[9], y, t[8] * x)) + t[11];
+  }
+}
+
+extern "C" int rfd_stn_apply(const float *grouped_xyz, const float *theta, int B, int M, int S, float *out, void *stream) {
+  if (B < 0 || M < 0 || S < 0) return RFD_ERR_INVALID_ARGUMENT;
+  if ((long long)B * M * S == 0) return RFD_OK;
+  if (!grouped_xyz || !theta || !out) return RFD_ERR_INVALID_ARGUMENT;
+  if (M > 65535 || B > 65535) return RFD_ERR_UNSUPPORTED_SIZE;
+  dim3 grid(h_ceil_div(S, 256) > 8 ? 8 : h_ceil_div(S, 256), M, B);
+  stn_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(grouped_xyz, theta, M, S, out);
+  RFD_CHECK_LAUNCH("stn_apply_kernel");
   return RFD_OK;
 }
 

@@ -682,7 +682,8 @@ extern "C" int rfd_mlp_chain(int mode, const float *x, int B, int K0, int L, con
   if (B < 0 || L < 0 || K0 < 1 || pool < 1) return RFD_ERR_INVALID_ARGUMENT;
   if (B == 0 || L == 0) return RFD_OK;
   if (!x || !packed || (!out_cm && !out_pm)) return RFD_ERR_INVALID_ARGUMENT;
-  if (!(pool == 1 || pool == 16 || pool == 32 || pool == 64 || pool == 128) || L % pool) return RFD_ERR_UNSUPPORTED_SIZE;
+  // pool: 1 (none), 16 / 32 (inside a warp's rows), or any power of two >= 64 (merged across warps / tiles with atomicMax)
+  if (!(pool == 1 || pool == 16 || pool == 32 || (pool >= 64 && (pool & (pool - 1)) == 0)) || L % pool) return RFD_ERR_UNSUPPORTED_SIZE;
   const ChainPlan p = chain_plan(mode, K0, 0, C1, C2, C3);
   if (!p.ok) return RFD_ERR_UNSUPPORTED_SIZE;
   ChainParams P = {};

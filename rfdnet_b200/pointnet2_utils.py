@@ -179,6 +179,26 @@ def fused_query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz=True,
     return out, gxyz, idx
 
 
+def _resample_uniformly(idx):
+    """`sample_uniformly` of the reference (pointnet2_utils.py:321-330): every row of idx (B,M,S) keeps its distinct
+    indices (ascending) and fills the remaining slots with uniform random draws from them.  Whole-tensor form on the
+    device (sort, first-occurrence mask, stable compaction, one randint) instead of the reference's B*M host loop.
+    -> (idx (B,M,S) i32, unique_cnt (B,M) f32)."""
+    B, M, S = idx.shape
+    srt, _ = torch.sort(idx.long(), dim=-1)
+    first = torch.ones_like(srt, dtype=torch.bool)
+    first[..., 1:] = srt[..., 1:] != srt[..., :-1]
+    cnt = first.sum(-1)                                                   # distinct indices per row
+    # stable compaction: distinct values to the front, in ascending order
+    order = torch.argsort((~first).to(torch.int8), dim=-1, stable=True)
+    uniq = torch.gather(srt, -1, order)
+    slot = torch.arange(S, device=idx.device).view(1, 1, S)
+    draw = (torch.rand((B, M, S), device=idx.device) * cnt.unsqueeze(-1)).long().clamp_(max=S - 1)
+    draw = torch.minimum(draw, (cnt - 1).unsqueeze(-1))
+    out = torch.where(slot < cnt.unsqueeze(-1), uniq, torch.gather(uniq, -1, draw))
+    return out.to(torch.int32), cnt.to(torch.float32)
+
+
 class QueryAndGroup(nn.Module):
     """pointnet2_utils.py:279-361.  Under autograd (training) the reference's op sequence runs on the
     drop-in kernels so gradients flow exactly as in the reference; without grad the fused kernel is used."""
@@ -206,16 +226,8 @@ class QueryAndGroup(nn.Module):
             return (new_features, grouped_xyz) if self.ret_grouped_xyz else new_features
 
         idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
-        if self.sample_uniformly:  # pointnet2_utils.py:321-330 (host loop, kept for API completeness)
-            unique_cnt = torch.zeros((idx.shape[0], idx.shape[1]))
-            for i_batch in range(idx.shape[0]):
-                for i_region in range(idx.shape[1]):
-                    unique_ind = torch.unique(idx[i_batch, i_region, :])
-                    num_unique = unique_ind.shape[0]
-                    unique_cnt[i_batch, i_region] = num_unique
-                    sample_ind = torch.randint(0, num_unique, (self.nsample - num_unique,), dtype=torch.long)
-                    all_ind = torch.cat((unique_ind, unique_ind[sample_ind]))
-                    idx[i_batch, i_region, :] = all_ind
+        if self.sample_uniformly:
+            idx, unique_cnt = _resample_uniformly(idx)
         xyz_trans = xyz.transpose(1, 2).contiguous()
         grouped_xyz = grouping_operation(xyz_trans, idx)
         grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)

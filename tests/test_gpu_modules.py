@@ -229,3 +229,44 @@ def test_full_sa_fusion_vs_materialised_fp32_path(N, npoint, radius, S, C, mlp):
     err, scale = float((f1 - f2).abs().max()), float(f1.abs().max())
     print(f"fused SA N={N} S={S} C={C}: max|err| {err:.3e} scale {scale:.3f}")
     assert err <= 1e-4 * max(1.0, scale)
+
+
+def test_stn_group_fused_path_vs_op_by_op_80k():
+    """The four-launch inference path of STN_Group (rotated grouping kernel, two tcgen05 chains, affine kernel) against
+    the module's own op-by-op autograd path (drop-in ball query / grouping + torch layers) on 80k-point scenes."""
+    from rfdnet_b200 import stn_group
+    _no_tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        stn = stn_group.STN_Group(radius=1.0, nsample=1024, use_xyz=False, normalize_xyz=True).eval()
+        seeded_fill(stn, 43, scale=0.3)
+        stn = stn.to(DEV)
+        pcs = torch.from_numpy(scannet_like_batch(2, 80000, seed0=61)).to(DEV)
+        xyz = pcs[..., :3].contiguous()
+        g = torch.Generator().manual_seed(8)
+        feats = torch.cat([pcs[..., 3:].transpose(1, 2), torch.randint(0, 9, (2, 1, 80000), generator=g).float().to(DEV)], 1).contiguous()
+        sel = torch.randint(0, 80000, (16,), generator=g)
+        box_xyz = (xyz[:, sel] + 0.1).contiguous()
+        heading = (torch.rand(2, 16, generator=g) * 6.28 - 3.14).to(DEV)
+        with torch.no_grad():
+            gx, gf = stn(xyz, feats, box_xyz, heading)                      # fused
+        with torch.enable_grad():
+            rx, rf = stn(xyz, feats, box_xyz, heading)                      # op by op (grad mode switches the path)
+        assert gx.shape == (2, 3, 16, 1024) and gf.shape == (2, 2, 16, 1024)
+        assert torch.equal(gf, rf.detach())                                 # gathered rows: exact
+        err = float((gx - rx.detach()).abs().max())
+        print(f"STN_Group fused vs op-by-op: max|err| {err:.2e} (coordinate scale {float(rx.abs().max()):.2f})")
+        assert err <= 2e-4
+        # use_xyz=True variant: the xyz channels of the features stay UNROTATED, as in the reference
+        stn2 = stn_group.STN_Group(radius=0.5, nsample=128, use_xyz=True, normalize_xyz=False).eval()
+        seeded_fill(stn2, 44, scale=0.3)
+        stn2 = stn2.to(DEV)
+        with torch.no_grad():
+            gx2, gf2 = stn2(xyz, feats, box_xyz, heading)
+        with torch.enable_grad():
+            rx2, rf2 = stn2(xyz, feats, box_xyz, heading)
+        assert gf2.shape == (2, 5, 16, 128) and torch.equal(gf2, rf2.detach())
+        assert float((gx2 - rx2.detach()).abs().max()) <= 2e-4
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = _no_tf32

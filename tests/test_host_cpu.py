@@ -152,6 +152,24 @@ def test_model_ref_golden_detection(golden):
     assert np.allclose(sc[:, :, -8:].numpy(), golden["det_sem_cls"], atol=1e-4, rtol=1e-4)
 
 
+def test_sample_uniformly_whole_tensor_form():
+    """QueryAndGroup(sample_uniformly=True), pointnet2_utils.py:321-330: distinct indices kept (ascending), the rest of
+    every row drawn from them."""
+    from rfdnet_b200.pointnet2_utils import _resample_uniformly
+    g = torch.Generator().manual_seed(0)
+    idx = torch.randint(0, 6, (3, 7, 16), generator=g, dtype=torch.int32)
+    idx[0, 0] = 4
+    idx[1, 2] = torch.arange(16, dtype=torch.int32)
+    out, cnt = _resample_uniformly(idx)
+    assert out.shape == idx.shape and out.dtype == torch.int32 and cnt.shape == (3, 7)
+    for b in range(3):
+        for m in range(7):
+            u = torch.unique(idx[b, m])
+            n = len(u)
+            assert cnt[b, m] == n and torch.equal(out[b, m, :n].long(), u.long())
+            assert set(out[b, m, n:].tolist()) <= set(u.tolist())
+
+
 def test_shard_range():
     from rfdnet_b200.dist import shard_range
     for n in (0, 1, 7, 8, 64, 257):
