@@ -73,6 +73,14 @@ __global__ void __launch_bounds__(MC_THREADS, 1) extract_mesh_kernel(const McPar
   const int R = P.R, Pd = R + 2, PP = Pd * Pd, NP = PP * Pd;
   unsigned int *info = reinterpret_cast<unsigned int *>(mc_smem);            // NP
   unsigned char *sign = mc_smem + (size_t)NP * 4;                           // NP
+  // the case tables are indexed by per-thread data: from constant memory every distinct address of a warp is a separate
+  // (serialised) fetch -- 0.5 ms per 256 objects in the first version of this kernel; shared memory serves them at once
+  __shared__ signed char s_tri_table[256][16];
+  __shared__ unsigned char s_tri_count[256];
+  __shared__ __align__(4) unsigned char s_edge_owner[12][4];
+  for (int e = threadIdx.x; e < 256 * 16; e += MC_THREADS) (&s_tri_table[0][0])[e] = (&c_tri_table[0][0])[e];
+  if (threadIdx.x < 256) s_tri_count[threadIdx.x] = c_tri_count[threadIdx.x];
+  if (threadIdx.x < 48) (&s_edge_owner[0][0])[threadIdx.x] = (&c_edge_owner[0][0])[threadIdx.x];
   __shared__ int s_scan_v[32], s_scan_t[32];
   __shared__ long long s_off[2];
   __shared__ int s_tot[2], s_fit;
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(MC_THREADS, 1) extract_mesh_kernel(const McPar
     int i = p0 / PP, r = p0 - i * PP, j = r / Pd, k = r - j * Pd;
     for (int p = p0; p < p1; ++p) {
       cv += __popc(edge_mask(p, i, j, k));
-      if (i + 1 < Pd && j + 1 < Pd && k + 1 < Pd) ct += c_tri_count[cube_index(p)];
+      if (i + 1 < Pd && j + 1 < Pd && k + 1 < Pd) ct += s_tri_count[cube_index(p)];
       if (++k == Pd) { k = 0; if (++j == Pd) { j = 0; ++i; } }
     }
   }
@@ -198,12 +206,13 @@ __global__ void __launch_bounds__(MC_THREADS, 1) extract_mesh_kernel(const McPar
     for (int p = p0; p < p1; ++p) {
       if (i + 1 < Pd && j + 1 < Pd && k + 1 < Pd) {
         const unsigned ci = cube_index(p);
-        const int n = c_tri_count[ci];
+        const int n = s_tri_count[ci];
         for (int t = 0; t < 3 * n; ++t) {
-          const int e = c_tri_table[ci][t];
-          const int q = p + c_edge_owner[e][0] * PP + c_edge_owner[e][1] * Pd + c_edge_owner[e][2];
+          const int e = s_tri_table[ci][t];
+          const uchar4 eo = *reinterpret_cast<const uchar4 *>(s_edge_owner[e]);
+          const int q = p + eo.x * PP + eo.y * Pd + eo.z;
           const unsigned w = info[q];
-          *tri++ = (int)((w & 0xfffffu) + __popc((w >> 20) & ((1u << c_edge_owner[e][3]) - 1u)));
+          *tri++ = (int)((w & 0xfffffu) + __popc((w >> 20) & ((1u << eo.w) - 1u)));
         }
       }
       if (++k == Pd) { k = 0; if (++j == Pd) { j = 0; ++i; } }
@@ -248,7 +257,7 @@ extern "C" int rfd_extract_mesh(const float *logits, int B, int R, double thresh
   P.vertices = vertices; P.vertex_f64 = vertex_f64; P.triangles = triangles;
   P.cap_v = cap_vertices; P.cap_t = cap_triangles; P.ranges = ranges; P.totals = totals;
   const int np = (R + 2) * (R + 2) * (R + 2);
-  const size_t smem = (size_t)np * 5 + 16;
+  const size_t smem = (size_t)np * 5 + 16;  // + 4.4 KB of static shared memory (tables)
   RFD_CHECK_CUDA(cudaFuncSetAttribute(extract_mesh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "extract_mesh attr");
   extract_mesh_kernel<<<B, MC_THREADS, smem, as_stream(stream)>>>(P);
