@@ -269,7 +269,7 @@ def run_gpu(args, rank, world, local):
                 raise
 
     if rank != 0:
-        return
+        return None
     # ---- per-kernel device times (CUDA events recorded around the launches inside the timed steps)
     dec = [(s.elapsed_time(e), w) for n, s, e, w in timers if n == "onet_decode"]
     dec_ms = float(np.mean([t for t, _ in dec]))
@@ -350,7 +350,7 @@ def run_gpu(args, rank, world, local):
         "train": train,
         "skip_propagation": skip,
     }
-    print(json.dumps(line))
+    return line
 
 
 def train_bench(args, rank, world, dev):
@@ -564,26 +564,27 @@ def main():
     if not os.path.exists(os.path.join(ROOT, "rfdnet_b200", "librfdnet_b200.so")):
         g.build()
     from rfdnet_b200 import dist as D
-    # NCCL prints its version banner on STDOUT when the first communicator is created; keep stdout for the one JSON
-    # line: route fd 1 to stderr during initialisation + the first collective, then restore it.
+    # NCCL (NCCL_DEBUG=INFO) logs on STDOUT whenever it initialises something -- the communicator, NVLS on the first
+    # all-reduce, the teardown.  stdout carries exactly ONE line, the JSON: fd 1 is routed to stderr for the whole run and
+    # the line is written to the saved descriptor at the end.
     sys.stdout.flush()
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
+    line = None
     try:
         D.init_from_env("nccl")
         if world > 1:
             torch.cuda.set_device(local)
             D.barrier()
             torch.cuda.synchronize()
+        line = run_gpu(args, rank, world, local)
+        if world > 1:
+            torch.distributed.destroy_process_group()
     finally:
         sys.stdout.flush()
-        os.dup2(saved_stdout, 1)
+        if line is not None:
+            os.write(saved_stdout, (json.dumps(line) + "\n").encode())
         os.close(saved_stdout)
-    run_gpu(args, rank, world, local)
-    if world > 1:
-        sys.stdout.flush()
-        os.dup2(2, 1)  # NCCL_DEBUG=INFO also logs the communicator teardown on stdout: keep it behind the JSON line
-        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

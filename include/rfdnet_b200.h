@@ -154,6 +154,17 @@ int rfd_mlp_chain_pack(int mode, int K0, int xyz, const float *W1, const float *
                        const float *scale3, const float *shift3, int C3, int relu_last, void *packed, void *stream);
 int rfd_mlp_chain(int mode, const float *x, int B, int K0, int L, const void *packed, int C1, int C2, int C3,
                   int relu_last, int pool, float *out_cm, float *out_pm, void *stream);
+/* rfd_mlp_chain with the options the wide PointNet-style encoders of SkipPropagation need (pointseg.py, layers.py:340-392):
+ *   relu_in     ReLU applied to x while it is loaded (ResnetBlockFC's leading activation)
+ *   gbias       (B, L/gbias_rows, n0) f32 or NULL: per-group pre-activation bias of layer 0, y = scale*(acc+gbias)+shift, n0 =
+ *               C1 rounded up to 64 (16 when C1 is the only layer) -- the contribution of a per-cloud constant input
+ *               (the max-pooled "global" half of a PointNet concat) without ever building the concatenated tensor
+ *   out_pool    (B, C_last, L/pool_rows) f32 or NULL, initialised by the caller (-inf): max over groups of pool_rows rows of
+ *               the unpooled output (pool must be 1), any sign; out_cm / out_pm may then both be NULL
+ * gbias_rows and pool_rows are multiples of the 128-row tile and divide L. */
+int rfd_mlp_chain_ex(int mode, const float *x, int B, int K0, int L, const void *packed, int C1, int C2, int C3,
+                     int relu_last, int pool, float *out_cm, float *out_pm, int relu_in, const float *gbias,
+                     int gbias_rows, float *out_pool, int pool_rows, void *stream);
 int rfd_sa_mlp_chain(int mode, const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx, int B, int N,
                      int M, int S, int C, float radius, int normalize_xyz, const void *packed, int C1, int C2, int C3,
                      float *out_cm, float *out_pm, void *stream);

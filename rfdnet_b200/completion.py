@@ -299,9 +299,16 @@ class SkipPropagation(nn.Module):
         return self.encoder(x).view(B, K, -1).transpose(1, 2), seg_pred, trans_feat
 
     def generate(self, box_xyz, box_orientations, box_feature, input_point_cloud):
+        """eval + no_grad + CUDA: STN_Group on its four fused launches, PointSeg and ResnetPointnet on the tcgen05 chain
+        kernel (completion_fast.encode; `self.fast_precision`: 'x3' fp32-grade default, 'fp16', or None = torch layers)."""
         xyz, feats = self._break_up_pc(input_point_cloud)
         feats = torch.cat([feats, torch.zeros_like(feats)], dim=1)  # instance labels are not used in generation
         xyz, feats = self.stn(xyz, feats, box_xyz, box_orientations)
+        mode = getattr(self, "fast_precision", "x3")
+        if (mode is not None and not self.training and not torch.is_grad_enabled() and xyz.is_cuda
+                and xyz.shape[-1] % 128 == 0 and self.encoder.block_0.size_h <= 512):
+            from . import completion_fast
+            return completion_fast.encode(self, xyz, feats, box_feature, mode)[0]
         return self._encode(xyz, feats, box_feature)[0]
 
     def forward(self, box_xyz, box_orientations, box_feature, input_point_cloud, point_instance_labels,

@@ -1,0 +1,169 @@
+"""SkipPropagation's dense networks at inference on the tcgen05 chain kernel (second half).
+
+Reference: models/iscnet/modules/skip_propagation.py:84-129 (`generate` -> PointSeg mask -> ResnetPointnet code),
+pointseg.py:7-168, layers.py:9-48,340-392.  For the 256 proposals of a scene these are 262 144 points through layers up to
+1088 -> 512 and 1024 -> 512 wide: 15.7 MFLOP per point, 4.1 TFLOP per scene -- in the reference (and in the torch mirror,
+completion.py) fp32 cuDNN / cuBLAS calls with every activation through HBM and the PointNet "global feature" materialised
+as a repeated tensor (B*K, 1024, n) and concatenated.
+
+Here every pointwise layer is a launch of rfd_mlp_chain_ex over ALL rows at once (x kept channel-major (C, R), so channel
+concatenation is adjacency in one buffer), and the algebra removes what does not need computing:
+  * a concatenated per-cloud constant (the max-pooled half of a PointNet concat) contributes W_b . pooled -- one value
+    per (cloud, output channel): it enters layer 0 as a per-group bias (gbias), the repeated tensor is never built and
+    the layer's K halves (1088 -> 64 for the segmentation head's first conv, 1024 -> 512 in the encoder blocks);
+  * ResnetBlockFC's `shortcut(x) + fc_1(h)` is ONE layer over the adjacent channels [x | h] with weights [W_s | W_1];
+  * max-pools come out of the producing kernel's epilogue (out_pool, sign-aware atomic max); layers whose rows are only
+    pooled (the 1024-wide PointNet heads) never write their rows;
+  * the leading ReLU of every residual block is applied while the operand is loaded (relu_in).
+8.6 MFLOP per point remain.  The per-cloud pieces (T-Net fully connected layers on 256 rows, the 3x3 / 64x64 alignments,
+the per-group bias products) are tiny and stay on torch.  Operand mode 'x3' (split fp16, fp32-grade) by default.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import mlp as _mlp
+
+
+def _conv_bn(conv, bn):
+    W, s, t = _mlp.fold_conv_bn(conv, bn)
+    return W, s, t
+
+
+def _lin(fc, cols=None):
+    W = fc.weight.detach().float()
+    W = W if cols is None else W[:, cols[0]:cols[1]]
+    b = fc.bias.detach().float() if fc.bias is not None else torch.zeros(W.shape[0], device=W.device)
+    return W.contiguous(), torch.ones_like(b), b.contiguous()
+
+
+class _Packed:
+    """packed tensor-core images of one SkipPropagation module, rebuilt when a parameter / buffer changes"""
+
+    def __init__(self, sp, mode):
+        self.mode = mode
+        ps, enc = sp.point_seg, sp.encoder
+        f = ps.feat
+        WL, CH = _mlp.WideLayer, _mlp.ChainMlp
+
+        def tnet(t):   # conv1 -> conv2 as one 2-layer chain, conv3 as a pooled-only wide layer
+            c12 = CH([(*_conv_bn(t.conv1, t.bn1), True), (*_conv_bn(t.conv2, t.bn2), True)], xyz=0, mode=mode)
+            return c12, WL(*_conv_bn(t.conv3, t.bn3), True, mode)
+
+        self.stn, self.fstn = tnet(f.stn), tnet(f.fstn)
+        self.conv1 = CH([(*_conv_bn(f.conv1, f.bn1), True)], xyz=0, mode=mode)
+        self.conv2 = CH([(*_conv_bn(f.conv2, f.bn2), True)], xyz=0, mode=mode)
+        self.conv3 = WL(*_conv_bn(f.conv3, f.bn3), False, mode)                      # bn3, NO ReLU, then max
+        W, s, t = _conv_bn(ps.conv1, ps.bn1)                                         # 1088 -> 512: [global 1024 | point 64]
+        self.seg_Wg = W[:, :1024].contiguous()
+        self.seg1 = WL(W[:, 1024:].contiguous(), s, t, True, mode)
+        self.seg234 = CH([(*_conv_bn(ps.conv2, ps.bn2), True), (*_conv_bn(ps.conv3, ps.bn3), True),
+                          (*_conv_bn(ps.conv4, None), False)], xyz=0, mode=mode)
+        # ResnetPointnet
+        self.fc_pos = WL(*_lin(enc.fc_pos), False, mode)
+        H = enc.block_0.size_h
+        self.blocks = []
+        for i in range(5):
+            b = getattr(enc, f"block_{i}")
+            if i == 0:
+                fc0 = WL(*_lin(b.fc_0), True, mode)                                  # K = 2H, no pooled half yet
+                Ws = b.shortcut.weight.detach().float()
+                Wcat = torch.cat([Ws, b.fc_1.weight.detach().float()], dim=1).contiguous()   # [x (2H) | h (H)]
+                self.blocks.append((fc0, None, WL(Wcat, *_lin(b.fc_1)[1:], False, mode), None))
+            else:
+                W0 = b.fc_0.weight.detach().float()
+                fc0 = WL(W0[:, :H].contiguous(), *_lin(b.fc_0)[1:], True, mode)
+                Ws = b.shortcut.weight.detach().float()
+                Wcat = torch.cat([Ws[:, :H], b.fc_1.weight.detach().float()], dim=1).contiguous()  # [net (H) | h (H)]
+                self.blocks.append((fc0, W0[:, H:].contiguous(), WL(Wcat, *_lin(b.fc_1)[1:], False, mode), Ws[:, H:].contiguous()))
+        self.H = H
+
+
+def _version(sp):
+    return tuple((t.data_ptr(), t._version) for t in list(sp.point_seg.parameters()) + list(sp.point_seg.buffers())
+                 + list(sp.encoder.parameters()) + list(sp.encoder.buffers()))
+
+
+def packed(sp, mode='x3'):
+    ver = (_version(sp), mode)
+    cache = getattr(sp, "_fast_packed", None)
+    if cache is None or cache[0] != ver:
+        cache = sp._fast_packed = (ver, _Packed(sp, mode))
+    return cache[1]
+
+
+def _tnet_matrix(t, pooled, k):
+    """fully connected tail of a T-Net on the pooled (BK, 1024) features -> (BK, k, k), identity added"""
+    x = F.relu(t.bn4(t.fc1(pooled)))
+    x = F.relu(t.bn5(t.fc2(x)))
+    x = t.fc3(x) + torch.eye(k, device=x.device, dtype=x.dtype).reshape(1, -1)
+    return x.view(-1, k, k)
+
+
+def _neg_inf(shape, dev):
+    return torch.full(shape, float("-inf"), dtype=torch.float32, device=dev)
+
+
+@torch.no_grad()
+def encode(sp, xyz, feats, box_feature, mode='x3'):
+    """SkipPropagation._encode (eval): xyz (B,3,K,n) aligned coordinates, feats (B,C,K,n) (channel 0 = height),
+    box_feature (B,128,K) -> (codes (B,c_dim,K), mask (B*K,n) bool)."""
+    P = packed(sp, mode)
+    B, _, K, n = xyz.shape
+    BK, R, dev = B * K, B * K * n, xyz.device
+    assert n % 128 == 0, "points per proposal must be a multiple of the 128-row tile"
+    f = sp.point_seg.feat
+
+    def rows(t):   # (B,C,K,n) -> (1,C,R) channel-major over all rows
+        return t.permute(1, 0, 2, 3).reshape(1, t.shape[1], R).contiguous()
+
+    pts = torch.cat([rows(xyz), rows(feats[:, :1])], dim=1)                          # (1,4,R): xyz', height
+
+    def tnet_pooled(pk, x):
+        c12, c3 = pk
+        h, _ = c12.dense(x)                                                         # (1,128,R)
+        pooled = _neg_inf((1, 1024, BK), dev)
+        c3(h, out=None, out_pool=pooled, pool_rows=n)                               # conv3 + bn + relu, max over the cloud
+        return pooled[0].t().contiguous()                                           # (BK,1024)
+
+    # ---- PointNetEncoder (pointseg.py:88-133)
+    trans = _tnet_matrix(f.stn, tnet_pooled(P.stn, pts), 3)                          # (BK,3,3)
+    p3 = pts[0, :3].view(3, BK, n).permute(1, 2, 0)                                  # (BK,n,3)
+    p3 = torch.bmm(p3, trans)                                                        # only the coordinates are rotated
+    x = torch.cat([p3.permute(2, 0, 1).reshape(1, 3, R), pts[:, 3:]], dim=1).contiguous()
+    x64, _ = P.conv1.dense(x)                                                        # (1,64,R)
+    tfeat = _tnet_matrix(f.fstn, tnet_pooled(P.fstn, x64), 64)                       # (BK,64,64)
+    pf = torch.bmm(x64[0].view(64, BK, n).permute(1, 2, 0), tfeat)                   # (BK,n,64)
+    pointfeat = pf.permute(2, 0, 1).reshape(1, 64, R).contiguous()
+    x128, _ = P.conv2.dense(pointfeat)
+    g = _neg_inf((1, 1024, BK), dev)
+    P.conv3(x128, out=None, out_pool=g, pool_rows=n)                                 # bn3(conv3), max (values of either sign)
+    g = g[0].t().contiguous()                                                        # (BK,1024) global feature
+    # ---- segmentation head: conv1 over [global (repeated) | pointfeat] = per-cloud bias + 64-wide layer
+    gb = (g @ P.seg_Wg.t()).view(1, BK, -1)                                          # (1,BK,512)
+    s1 = torch.empty((1, 512, R), dtype=torch.float32, device=dev)
+    P.seg1(pointfeat, out=s1, gbias=gb, gbias_rows=n)
+    logit, _ = P.seg234.dense(s1)                                                    # (1,2,R)
+    mask = (logit[0, 1] > logit[0, 0]).view(BK, n)                                   # argmax of log_softmax (ties -> class 0)
+    # ---- ResnetPointnet (layers.py:340-392) on mask * [xyz', height, box feature]
+    box = box_feature.permute(1, 0, 2).reshape(-1, BK)                               # (128,BK)
+    xin = torch.cat([pts[0], box.unsqueeze(-1).expand(-1, -1, n).reshape(-1, R)], dim=0)
+    xin = (xin * mask.view(1, R).to(xin.dtype)).unsqueeze(0).contiguous()            # (1,132,R)
+    H = P.H
+    cur = torch.empty((1, 3 * H, R), dtype=torch.float32, device=dev)                # block 0: [net0 (2H) | h (H)]
+    P.fc_pos(xin, out=cur[:, :2 * H])
+    pooled = None
+    for i, (fc0, W0b, cat, Wsb) in enumerate(P.blocks):
+        kin = 2 * H if i == 0 else H
+        gb0 = gbs = None
+        if i > 0:
+            rp = F.relu(pooled)                                                      # (BK,H): relu of the appended half
+            gb0, gbs = (rp @ W0b.t()).view(1, BK, -1), (rp @ Wsb.t()).view(1, BK, -1)
+        fc0(cur[:, :kin], out=cur[:, kin:kin + H], relu_in=True, gbias=gb0, gbias_rows=n)
+        nxt = torch.empty((1, 2 * H, R), dtype=torch.float32, device=dev) if i < 4 else None
+        pl = _neg_inf((1, H, BK), dev)
+        cat(cur[:, :kin + H], out=None if nxt is None else nxt[:, :H], relu_in=True, gbias=gbs, gbias_rows=n,
+            out_pool=pl, pool_rows=n)
+        pooled = pl[0].t().contiguous()
+        cur = nxt
+    codes = sp.encoder.fc_c(F.relu(pooled))                                          # (BK,c_dim)
+    return codes.view(B, K, -1).transpose(1, 2), mask

@@ -98,7 +98,19 @@ struct ChainParams {
   int nsteps;
   ChainStep st[CH_MAX_STEPS];
   int tiles_per_scene, num_tiles;
+  // dense-mode extras (rfd_mlp_chain_ex)
+  int relu_in;            // ReLU applied to the layer-0 input while it is loaded
+  const float *gbias;     // (B, L / gbias_rows, n0) per-group pre-activation bias of layer 0: y = scale * (acc + gbias) + shift
+  int gbias_rows;         // rows per group (multiple of the 128-row tile)
+  float *out_pool;        // (B, out_C, L / pool_rows): max over groups of rows of the (unpooled) output, caller-initialised
+  int pool_rows;          //   to -inf; merged with a sign-aware atomic max (values of either sign)
 };
+
+// atomic max on a float of either sign (address initialised to -inf or any float)
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
 
 template <int MODE>
 __device__ __forceinline__ void chain_store_act(uint32_t addr, float v0, float v1, bool relu) {
@@ -313,6 +325,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
             for (int u = 0; u < 8; ++u) {
               const int c = r * CH_APAN * 64 + c8 * 8 + u;
               f[u] = (rv && c < P.K0) ? __ldg(xb + (size_t)c * P.L) : 0.f;
+              if (P.relu_in) f[u] = fmaxf(f[u], 0.f);
             }
             chain_store_chunk<MODE>(a_base + (c8 >> 3) * CH_PANEL + row * 128 + (((c8 & 7) ^ (row & 7)) << 4), f);
           }
@@ -334,6 +347,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
         const uint32_t tmem_s = tmem_base + (uint32_t)((s & 1) * 256);
         const bool xyz_term = s == 0 && P.has_xyz;
         const bool no_acc = s == 0 && kp0 == 0;  // xyz-only layer: nothing was accumulated in TMEM
+        // per-group bias of layer 0 (a tile never straddles groups: gbias_rows is a multiple of the tile height)
+        const float *gbp = (s == 0 && P.gbias) ? P.gbias + ((size_t)b * (P.L / P.gbias_rows) + l0 / P.gbias_rows) * S.n : nullptr;
         float4 rel[4];
         if (xyz_term) {
 #pragma unroll
@@ -352,6 +367,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
           const int t0 = S.tab_off + cb + 2 * lc;
           const float2 a0 = umma::lds_f2(scale_a + t0 * 4), a1 = umma::lds_f2(scale_a + (t0 + 8) * 4);
           const float2 s0 = umma::lds_f2(shift_a + t0 * 4), s1 = umma::lds_f2(shift_a + (t0 + 8) * 4);
+          float2 gb0 = make_float2(0.f, 0.f), gb1 = gb0;
+          if (gbp) {
+            gb0 = __ldg(reinterpret_cast<const float2 *>(gbp + cb + 2 * lc));
+            gb1 = __ldg(reinterpret_cast<const float2 *>(gbp + cb + 8 + 2 * lc));
+          }
           umma::tc_wait_ld();
           // y[i][j][u]: column cb + 8i + 2lc + u, row 32q + lr + 8j
           float y[2][4][2];
@@ -363,6 +383,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
 #pragma unroll
               for (int u = 0; u < 2; ++u) {
                 float acc = no_acc ? 0.f : __uint_as_float(v[j >> 1][4 * i + 2 * (j & 1) + u]);
+                if (gbp) acc += u ? (i ? gb1.y : gb0.y) : (i ? gb1.x : gb0.x);
                 if (xyz_term) {
                   const float4 w = s_wxyz[cb + 8 * i + 2 * lc + u];
                   acc = __fmaf_rn(w.x, rel[j].x, __fmaf_rn(w.y, rel[j].y, __fmaf_rn(w.z, rel[j].z, acc)));
@@ -381,6 +402,33 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
             }
           } else if (gpool == 1) {
             // ---- dense output rows
+            if (P.out_pool) {
+              // max over the tile's rows per column (warp: 32 rows), merged across warps / tiles by the sign-aware atomic
+              const int grp = l0 / P.pool_rows, ngrp = P.L / P.pool_rows;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                float m0v = -INFINITY, m1v = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (l0 + q * 32 + lr + 8 * j < P.L) {
+                    float y0 = y[i][j][0], y1 = y[i][j][1];
+                    if (S.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+                    m0v = fmaxf(m0v, y0); m1v = fmaxf(m1v, y1);
+                  }
+                }
+#pragma unroll
+                for (int off = 4; off <= 16; off <<= 1) {
+                  m0v = fmaxf(m0v, __shfl_xor_sync(0xffffffffu, m0v, off));
+                  m1v = fmaxf(m1v, __shfl_xor_sync(0xffffffffu, m1v, off));
+                }
+                const int col = cb + 8 * i + 2 * lc;
+                if (lr == 0 && m0v > -INFINITY) {
+                  float *o = P.out_pool + ((size_t)b * P.out_C + S.out_ch0 + col) * ngrp + grp;
+                  if (col < S.out_valid) atomic_max_float(o, m0v);
+                  if (col + 1 < S.out_valid) atomic_max_float(o + ngrp, m1v);
+                }
+              }
+            }
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const int col = cb + 8 * i + 2 * lc;
@@ -677,18 +725,29 @@ static int chain_launch(int mode, ChainParams &P, const ChainPlan &p, const void
   return RFD_OK;
 }
 
-extern "C" int rfd_mlp_chain(int mode, const float *x, int B, int K0, int L, const void *packed, int C1, int C2, int C3,
-                             int relu_last, int pool, float *out_cm, float *out_pm, void *stream) {
+extern "C" int rfd_mlp_chain_ex(int mode, const float *x, int B, int K0, int L, const void *packed, int C1, int C2, int C3,
+                                int relu_last, int pool, float *out_cm, float *out_pm, int relu_in, const float *gbias,
+                                int gbias_rows, float *out_pool, int pool_rows, void *stream) {
   if (B < 0 || L < 0 || K0 < 1 || pool < 1) return RFD_ERR_INVALID_ARGUMENT;
   if (B == 0 || L == 0) return RFD_OK;
-  if (!x || !packed || (!out_cm && !out_pm)) return RFD_ERR_INVALID_ARGUMENT;
+  if (!x || !packed || (!out_cm && !out_pm && !out_pool)) return RFD_ERR_INVALID_ARGUMENT;
+  if (gbias && (gbias_rows < CH_TILE_M || gbias_rows % CH_TILE_M || L % gbias_rows)) return RFD_ERR_UNSUPPORTED_SIZE;
+  if (out_pool && (pool != 1 || pool_rows < CH_TILE_M || pool_rows % CH_TILE_M || L % pool_rows)) return RFD_ERR_UNSUPPORTED_SIZE;
   // pool: 1 (none), 16 / 32 (inside a warp's rows), or any power of two >= 64 (merged across warps / tiles with atomicMax)
   if (!(pool == 1 || pool == 16 || pool == 32 || (pool >= 64 && (pool & (pool - 1)) == 0)) || L % pool) return RFD_ERR_UNSUPPORTED_SIZE;
   const ChainPlan p = chain_plan(mode, K0, 0, C1, C2, C3);
   if (!p.ok) return RFD_ERR_UNSUPPORTED_SIZE;
   ChainParams P = {};
   P.x = x; P.K0 = K0; P.M = L / pool; P.S = pool;
+  P.relu_in = relu_in; P.gbias = gbias; P.gbias_rows = gbias_rows; P.out_pool = out_pool; P.pool_rows = pool_rows;
   return chain_launch(mode, P, p, packed, relu_last, B, L, pool, out_cm, out_pm, stream);
+}
+
+extern "C" int rfd_mlp_chain(int mode, const float *x, int B, int K0, int L, const void *packed, int C1, int C2, int C3,
+                             int relu_last, int pool, float *out_cm, float *out_pm, void *stream) {
+  if (!out_cm && !out_pm) return (B == 0 || L == 0) ? RFD_OK : RFD_ERR_INVALID_ARGUMENT;
+  return rfd_mlp_chain_ex(mode, x, B, K0, L, packed, C1, C2, C3, relu_last, pool, out_cm, out_pm, 0, nullptr, 0, nullptr, 0,
+                          stream);
 }
 
 extern "C" int rfd_sa_mlp_chain(int mode, const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx, int B,

@@ -93,6 +93,8 @@ class ChainMlp:
         self.K0 = layers[0][0].shape[1] - self.xyz
         self.C = [l[0].shape[0] for l in layers] + [0] * (3 - n)
         self.out_C = layers[-1][0].shape[0]
+        # padded width of layer 0's accumulator (the row length of a gbias table)
+        self.n0 = (self.C[0] + 63) // 64 * 64 if n > 1 else (min(self.C[0], 256) + 15) // 16 * 16
         self.flop_per_row = 2.0 * sum(l[0].shape[0] * l[0].shape[1] for l in layers)
         lib = _lib.load()
         nbytes = lib.rfd_mlp_chain_packed_bytes(self.mode, self.K0, self.xyz, *self.C)
@@ -120,16 +122,28 @@ class ChainMlp:
         pm = torch.empty((B, rows, self.out_C), dtype=torch.float32, device=dev) if want_pm else None
         return cm, pm
 
-    def dense(self, x, pool=1, want_cm=True, want_pm=False):
-        """x (B, K0, L) f32 channel-major -> (out_cm (B, C, L/pool) | None, out_pm (B, L/pool, C) | None)."""
+    def dense(self, x, pool=1, want_cm=True, want_pm=False, relu_in=False, gbias=None, gbias_rows=0, out_cm=None,
+              out_pool=None, pool_rows=0):
+        """x (B, K0, L) f32 channel-major -> (out_cm (B, C, L/pool) | None, out_pm (B, L/pool, C) | None).
+        relu_in / gbias (B, L/gbias_rows, n0) / out_pool (B, C, L/pool_rows, caller-initialised to -inf): see
+        rfd_mlp_chain_ex.  out_cm: write into this preallocated (B, C, L/pool) contiguous view instead of a new tensor."""
         check_f32(x, "x")
         B, K0, L = x.shape
         assert K0 == self.K0 and self.xyz == 0, (K0, self.K0)
-        cm, pm = self._outs(B, L // pool, x.device, want_cm, want_pm)
+        cm, pm = self._outs(B, L // pool, x.device, want_cm and out_cm is None, want_pm)
+        if out_cm is not None:
+            assert out_cm.shape == (B, self.out_C, L // pool) and out_cm.is_contiguous() and out_cm.dtype == torch.float32
+            cm = out_cm
+        if gbias is not None:
+            check_f32(gbias, "gbias")
+            assert gbias.shape[0] == B and gbias.shape[1] == L // gbias_rows and gbias.shape[2] == self.n0, (gbias.shape, self.n0)
+        if out_pool is not None:
+            assert out_pool.shape == (B, self.out_C, L // pool_rows) and out_pool.is_contiguous()
         with torch.cuda.device(x.device), _lib.timed("mlp_chain_tc", B * L * self.flop_per_row):
-            _lib.check(_lib.load().rfd_mlp_chain(self.mode, x.data_ptr(), B, K0, L, self.packed.data_ptr(), *self.C,
-                                                 self.relu_last, int(pool), _ptr(cm), _ptr(pm),
-                                                 torch.cuda.current_stream().cuda_stream), "mlp_chain")
+            _lib.check(_lib.load().rfd_mlp_chain_ex(self.mode, x.data_ptr(), B, K0, L, self.packed.data_ptr(), *self.C,
+                                                    self.relu_last, int(pool), _ptr(cm), _ptr(pm), int(bool(relu_in)),
+                                                    _ptr(gbias), int(gbias_rows), _ptr(out_pool), int(pool_rows),
+                                                    torch.cuda.current_stream().cuda_stream), "mlp_chain")
         return cm, pm
 
     def gather(self, xyz, new_xyz, feat_pm, idx, radius, normalize_xyz, want_cm=True, want_pm=False):
@@ -150,6 +164,36 @@ class ChainMlp:
                 float(radius), int(bool(normalize_xyz)), self.packed.data_ptr(), *self.C, _ptr(cm), _ptr(pm),
                 torch.cuda.current_stream().cuda_stream), "sa_mlp_chain")
         return cm, pm
+
+
+class WideLayer:
+    """ONE pointwise layer of any input / output width on the tcgen05 chain kernel, for the PointNet-style encoders of
+    SkipPropagation (widths up to 1088 -> 1024): the output channels are split into blocks of <= 256, one single-layer
+    chain launch per block, every launch streaming the whole K through the resident A panels.  Rows of all clouds are one
+    batch: x (1, K, R) channel-major, so a block's output is the contiguous slice out[:, c0:c1, :]."""
+
+    def __init__(self, W, scale, shift, relu, mode='x3', block=256):
+        self.Cout, self.K = W.shape
+        self.blocks = []
+        for c0 in range(0, self.Cout, block):
+            c1 = min(self.Cout, c0 + block)
+            ch = ChainMlp([(W[c0:c1].contiguous(), scale[c0:c1].contiguous(), shift[c0:c1].contiguous(), bool(relu))],
+                          xyz=0, mode=mode)
+            assert ch.ok, (W.shape, c0, c1)
+            self.blocks.append((c0, c1, ch))
+
+    def __call__(self, x, out=None, relu_in=False, gbias=None, gbias_rows=0, out_pool=None, pool_rows=0):
+        """x (1,K,R) -> out (1,Cout,R) (given, or None = do not write the rows) ; gbias (1,G,Cout) ; out_pool (1,Cout,G')"""
+        assert x.shape[0] == 1 and x.shape[1] == self.K, (x.shape, self.K)
+        for c0, c1, ch in self.blocks:
+            gb = None
+            if gbias is not None:
+                gb = torch.zeros((1, gbias.shape[1], ch.n0), dtype=torch.float32, device=x.device)
+                gb[:, :, :c1 - c0] = gbias[:, :, c0:c1]
+            ch.dense(x, want_cm=False, relu_in=relu_in, gbias=gb, gbias_rows=gbias_rows,
+                     out_cm=None if out is None else out[:, c0:c1, :],
+                     out_pool=None if out_pool is None else out_pool[:, c0:c1, :], pool_rows=pool_rows)
+        return out
 
 
 def check_f32(t, name):

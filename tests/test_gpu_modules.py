@@ -270,3 +270,46 @@ def test_stn_group_fused_path_vs_op_by_op_80k():
         assert float((gx2 - rx2.detach()).abs().max()) <= 2e-4
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = _no_tf32
+
+
+@pytest.mark.parametrize("mode,tol", [("x3", 2e-4), ("fp16", 3e-2)])
+def test_skip_propagation_generate_tensor_core_vs_torch(mode, tol):
+    """SkipPropagation.generate: PointSeg + ResnetPointnet on the tcgen05 chain kernel (per-cloud biases instead of
+    repeated global features, fused shortcut, epilogue max-pools) against the mirror's torch layers (fp32, TF32 off)."""
+    from rfdnet_b200 import completion, completion_fast
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sp = completion.SkipPropagation(input_feature_dim=1, c_dim=512, hidden_dim=512).eval()
+        seeded_fill(sp, 23)
+        sp = sp.to(DEV)
+        pc = torch.from_numpy(scannet_like_batch(2, 30000, seed0=77)).to(DEV)
+        g = torch.Generator().manual_seed(4)
+        sel = torch.randint(0, 30000, (6,), generator=g)
+        box_xyz = (pc[:, sel, :3] + 0.05).contiguous()
+        heading = (torch.rand(2, 6, generator=g) * 6.28).to(DEV)
+        box_feat = torch.randn(2, 128, 6, generator=g).to(DEV)
+        with torch.no_grad():
+            sp.fast_precision = None
+            ref = sp.generate(box_xyz, heading, box_feat, pc)
+            sp.fast_precision = mode
+            out = sp.generate(box_xyz, heading, box_feat, pc)
+            # the masks of both paths (a flipped near-tie moves a whole point in or out of the encoder's input)
+            xyz, feats = sp._break_up_pc(pc)
+            feats = torch.cat([feats, torch.zeros_like(feats)], dim=1)
+            gx, gf = sp.stn(xyz, feats, box_xyz, heading)
+            _, mask = completion_fast.encode(sp, gx, gf, box_feat, mode)
+            pts = torch.cat([gx, gf[:, :1]], dim=1).permute(0, 2, 3, 1).contiguous().view(12, 1024, -1)
+            seg, _ = sp.point_seg(pts.transpose(1, 2).contiguous())
+            mask_ref = torch.argmax(seg.view(12, 1024, 2), dim=-1).bool()
+        flips = float((mask != mask_ref).float().mean())
+        scale = float(ref.abs().max())
+        err = float((out - ref).abs().max())
+        print(f"SkipPropagation.generate {mode}: max|err| {err:.2e} (code scale {scale:.2f}), mask flips {flips:.2e}, "
+              f"masked-in fraction {float(mask_ref.float().mean()):.2f}")
+        assert out.shape == ref.shape == (2, 512, 6)
+        assert flips <= (1e-3 if mode == "x3" else 2e-2)
+        assert err <= tol * max(1.0, scale) or (flips > 0 and err <= 50 * tol * max(1.0, scale))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
