@@ -455,10 +455,16 @@ def skip_propagation_bench(dev, pc, ep):
 
     stn_ms, _ = timed(lambda: sp.stn(xyz, feats, box_xyz, heading))
     tot_ms, codes = timed(lambda: sp.generate(box_xyz, heading, box_feat, pc1), n=2)
+    sp.fast_precision = None
+    torch_ms, codes_t = timed(lambda: sp.generate(box_xyz, heading, box_feat, pc1), n=1)
     out = {"proposals": 256, "points": int(pc1.shape[1]), "nsample": 1024, "stn_group_ms": stn_ms, "generate_ms": tot_ms,
+           "generate_torch_layers_ms": torch_ms, "max_abs_diff_vs_torch_layers": float((codes - codes_t).abs().max()),
            "codes_shape": list(codes.shape), "codes_finite": bool(torch.isfinite(codes).all()),
-           "note": "stn_group_ms: rfd_query_and_group_rotated + 2 x rfd_mlp_chain (tcgen05, x3) + rfd_stn_apply; the rest of "
-                   "generate_ms is PointSeg + ResnetPointnet on torch (fp32 library GEMMs)"}
+           "note": "generate_ms: STN_Group (rfd_query_and_group_rotated + 2 x rfd_mlp_chain + rfd_stn_apply) + PointSeg + "
+                   "ResnetPointnet on the tcgen05 chain kernel (rfd_mlp_chain_ex, x3 = fp32-grade operands, 8.6 MFLOP per "
+                   "point after folding the repeated global features into per-cloud biases); generate_torch_layers_ms: the "
+                   "same with PointSeg / ResnetPointnet on torch fp32 library GEMMs (the reference's formulation, 15.7 MFLOP "
+                   "per point)"}
     del sp
     torch.cuda.empty_cache()
     return out
