@@ -25,6 +25,7 @@
 //            32 consecutive slots as one 128-byte coalesced store.  No per-element index arithmetic, no div/mod.
 // None of the reference's four intermediate passes over the grouped tensor exists.
 #include <atomic>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -532,6 +533,7 @@ struct QgParams {
   const float4 *gsorted;
   int cloud_pts;                                   // staged points per pass (multiple of 128), 0 in grid mode
   const float *heading;                            // (B, M) or nullptr: rotate the relative xyz about z by -heading (STN_Group)
+  int nbuf;                                        // transposition buffers per warp: 2 = loads of step it+1 overlap step it
 };
 
 constexpr int QG_MAX_G = 4;
@@ -591,7 +593,7 @@ query_and_group_kernel(const QgParams P) {
   const uint32_t area1 = P.gs ? (uint32_t)(BQ_WARPS * GRID_CAP * 4) : (uint32_t)P.cloud_pts * 12u;
   const uint32_t idx_a = sm0 + 16 + ((area1 + 15u) & ~15u) + (uint32_t)warp * (uint32_t)(G * S) * 4u;
   const uint32_t idx_end = sm0 + 16 + ((area1 + 15u) & ~15u) + (uint32_t)BQ_WARPS * (uint32_t)(G * S) * 4u;
-  const uint32_t tile = ((idx_end + 127u) & ~127u) + (uint32_t)warp * (2 * QG_TILE);  // two 4-KB buffers per warp
+  const uint32_t tile = ((idx_end + 127u) & ~127u) + (uint32_t)warp * (uint32_t)(P.nbuf * QG_TILE);  // nbuf 4-KB buffers per warp
 
   const float *xyz = P.xyz + (size_t)b * n * 3;
   const float *new_xyz = P.new_xyz + (size_t)b * m * 3;
@@ -744,7 +746,7 @@ query_and_group_kernel(const QgParams P) {
       // flight per warp: the loads of step it+1 are issued before step it is transposed out, hiding the L2 latency.
       // (tile, channel block) of a step advance incrementally (no integer division in the loop)
       auto issue = [&](int it, int t, int c0) {
-        const uint32_t buf = tile + (uint32_t)(it & 1) * QG_TILE;
+        const uint32_t buf = tile + (uint32_t)(it & (P.nbuf - 1)) * QG_TILE;
         if (c0 + 4 * jl < Cp) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -763,14 +765,14 @@ query_and_group_kernel(const QgParams P) {
       for (int it = 0; it < nit; ++it) {
         int tn = t, cn = c0 + 32;   // step it + 1
         if (cn >= (nc0 << 5)) { cn = 0; ++tn; }
-        if (it + 1 < nit) {
+        if (it + 1 < nit && P.nbuf == 2) {
           issue(it + 1, tn, cn);
           asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
           asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncwarp();
-        const uint32_t ld_base = tile + (uint32_t)(it & 1) * QG_TILE + ld_off;
+        const uint32_t ld_base = tile + (uint32_t)(it & (P.nbuf - 1)) * QG_TILE + ld_off;
         const int myslot = t * 32 + lane;
         const bool sv = myslot < nslots;
         float *oc = o + (size_t)c0 * MS + myslot;
@@ -799,6 +801,7 @@ query_and_group_kernel(const QgParams P) {
           }
         }
         __syncwarp();  // the buffer is free for the loads of step it + 2
+        if (P.nbuf == 1 && it + 1 < nit) issue(it + 1, tn, cn);
         t = tn; c0 = cn;
       }
     }
@@ -1003,7 +1006,8 @@ static int query_and_group_impl(const float *xyz, const float *new_xyz, const fl
   P.cloud_pts = use_grid ? 0 : (N < QG_CHUNK ? ((N + 127) & ~127) : QG_CHUNK);
   size_t smem = 16 + (((use_grid ? (size_t)BQ_WARPS * GRID_CAP * 4 : (size_t)P.cloud_pts * 12) + 15) & ~(size_t)15);
   smem += (size_t)BQ_WARPS * G * nsample * 4;
-  smem += 128 + (transposed ? (size_t)BQ_WARPS * 2 * QG_TILE : 0);
+  P.nbuf = 2;  // measured: 1 buffer (3 CTAs/SM instead of 2) is 1 % faster at SA2 and 8-10 % slower at SA3 / SA4 / vote-agg
+  smem += 128 + (transposed ? (size_t)BQ_WARPS * P.nbuf * QG_TILE : 0);
   RFD_CHECK_CUDA(cudaFuncSetAttribute(query_and_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024),
                  "query_and_group attr");
   const int tasks = h_ceil_div(M, G);

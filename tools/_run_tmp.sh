@@ -1,4 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_modules.py -m gpu -x -q -s -k "skip_propagation" 2>&1 | tail -12
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-train 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value']); print(d['skip_propagation'])"
+for nb in 2 1 2 1; do RFD_QG_NBUF=$nb timeout 300 python tools/prof_qg.py 4 30 2>&1 | sed "s/^/nbuf=$nb /"; done | tee gpurun_out/r2v_qg.log
+RFD_QG_NBUF=1 timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "fused or group" 2>&1 | tail -2
