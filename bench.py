@@ -100,11 +100,11 @@ def bind_to_gpu_numa_node(index):
     return 0
 
 
-def build_model(device, seed=0, backbone_precision="x3", head_precision="x3", decoder_precision="fp16"):
+def build_model(device, seed=0, backbone_precision="x3", head_precision="x3", decoder_precision="fp16", graph=False):
     from rfdnet_b200.pipeline import SceneHotPath
     from rfdnet_b200.synth import seeded_fill
     net = SceneHotPath(precision=decoder_precision, backbone_precision=backbone_precision,
-                       head_precision=head_precision).eval()
+                       head_precision=head_precision, graph_detection=graph).eval()
     seeded_fill(net, seed)
     return net.to(device)
 
@@ -196,7 +196,7 @@ def run_gpu(args, rank, world, local):
     bind_to_gpu_numa_node(phys)
     S = args.scenes
     net = build_model(dev, backbone_precision=args.backbone_precision, head_precision=args.head_precision,
-                      decoder_precision=args.decoder_precision)
+                      decoder_precision=args.decoder_precision, graph=args.graph_detection)
     sets = [make_inputs(S, 1000 * rank + 100 * i) for i in range(2)]  # two rotating input sets
     dev_sets = [(pc.to(dev), codes.to(dev)) for pc, codes in sets]
     host_sets = [(pc.pin_memory(), codes.pin_memory()) for pc, codes in sets]
@@ -238,14 +238,14 @@ def run_gpu(args, rank, world, local):
     # scores; the variant that ships every logit to the host (round 1's e2e) is timed as well.
     def e2e_run(result):
         for i in range(3):
-            net.run_host(*host_sets[i & 1], logits_host, dev, result=result)
+            net.run_host(*host_sets[i & 1], logits_host, dev, result=result, chunks=args.e2e_chunks)
         torch.cuda.synchronize()
         D.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         h2d = d2h = 0
         for i in range(args.steps):
-            h2d, d2h = net.run_host(*host_sets[i & 1], logits_host, dev, result=result)
+            h2d, d2h = net.run_host(*host_sets[i & 1], logits_host, dev, result=result, chunks=args.e2e_chunks)
             torch.cuda.synchronize()  # the step's result is on the host before the next step starts
         t = time.perf_counter() - t0
         D.barrier()
@@ -321,6 +321,7 @@ def run_gpu(args, rank, world, local):
                                "vote/proposal MLPs: %s]" % (dec_mode, args.backbone_precision, args.head_precision),
                    "scenes_per_gpu_per_step": S, "points": 80000, "proposals": 256, "grid": 32,
                    "parallelism": f"dp{world} (scenes sharded, no collective)",
+                   "detection_launch": "one CUDA graph" if args.graph_detection else "eager (45 launches)", "e2e_chunks": args.e2e_chunks,
                    "l2": "per-step working set (logits %d MB + clouds) exceeds the 126 MB L2; inputs rotate over 2 sets"
                          % (S * 256 * 32768 * 4 // 2 ** 20)},
         "roofline": {"kernel": "onet_decode_kernel", "bound": "tensor", "achieved": dec_tflops, "peak": tc_sust,
@@ -546,6 +547,8 @@ def main():
     ap.add_argument("--scenes", type=int, default=4, help="scenes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the config-5 training-step block")
+    ap.add_argument("--graph-detection", action="store_true", help="replay the detection pass as one CUDA graph")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="object chunks of the decoder in the end-to-end call")
     ap.add_argument("--train-batch", type=int, default=8, help="scenes per GPU per training step (config 5: 8)")
     ap.add_argument("--train-steps", type=int, default=3)
     ap.add_argument("--bucket-mb", type=int, default=8, help="gradient all-reduce bucket size")

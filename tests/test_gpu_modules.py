@@ -321,3 +321,31 @@ def test_skip_propagation_generate_tensor_core_vs_torch(mode, tol):
         assert err <= tol * max(1.0, scale) or (flips > 0 and err <= 50 * tol * max(1.0, scale))
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+
+
+def test_detection_as_one_cuda_graph_equals_eager():
+    """the whole detection pass replayed as one CUDA graph gives the eager pass's tensors bit for bit,
+    for every input of the captured shape (the FPS prefix proof is a device-side flag, not a host decision)."""
+    from rfdnet_b200.pipeline import GraphedDetection
+    net = detection.DetectionHotPath(1, 256).eval()
+    seeded_fill(net, 5)
+    net = net.to(DEV)
+    graphed = GraphedDetection(net)
+    for seed in (11, 12, 13):
+        pc = torch.from_numpy(scannet_like_batch(2, 30000, seed0=seed)).to(DEV)
+        with torch.no_grad():
+            ep_e, _ = net(pc)
+            ep_e = {k: v.clone() for k, v in ep_e.items()}
+            ep_g, _ = graphed(pc)
+        for k in ("sa1_inds", "sa2_inds", "fp2_features", "vote_xyz", "aggregated_vote_inds", "objectness_scores", "center",
+                  "sem_cls_scores"):
+            assert torch.equal(ep_e[k], ep_g[k]), (seed, k)
+    assert len(graphed.cache) == 1
+    # a cloud whose first 2048 samples are NOT in FPS order for SA2 (duplicated points => ties): the flag path still agrees
+    pc = torch.from_numpy(scannet_like_batch(2, 30000, seed0=14)).to(DEV)
+    pc[:, 1::2] = pc[:, 0::2]
+    with torch.no_grad():
+        ep_e, _ = net(pc)
+        ep_e = {k: v.clone() for k, v in ep_e.items()}
+        ep_g, _ = graphed(pc)
+    assert torch.equal(ep_e["sa2_inds"], ep_g["sa2_inds"]) and torch.equal(ep_e["objectness_scores"], ep_g["objectness_scores"])
