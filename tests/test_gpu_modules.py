@@ -349,3 +349,34 @@ def test_detection_as_one_cuda_graph_equals_eager():
         ep_e = {k: v.clone() for k, v in ep_e.items()}
         ep_g, _ = graphed(pc)
     assert torch.equal(ep_e["sa2_inds"], ep_g["sa2_inds"]) and torch.equal(ep_e["objectness_scores"], ep_g["objectness_scores"])
+
+
+@pytest.mark.parametrize("mode", ["x3", "fp16"])
+def test_chain_ex_relu_in_group_bias_and_epilogue_pool(mode):
+    """rfd_mlp_chain_ex: ReLU on the loaded operand, per-group pre-activation bias, and the max over groups of rows taken in
+    the epilogue (values of either sign), against plain torch; WideLayer splits a 600-wide output into column blocks."""
+    from rfdnet_b200 import mlp
+    g = torch.Generator().manual_seed(12)
+    K, C, R, rows = 200, 600, 3 * 256 + 128, 128          # 7 groups of 128 rows
+    G = R // rows
+    W = (torch.randn(C, K, generator=g) / K ** 0.5).to(DEV)
+    s = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    t = (torch.randn(C, generator=g) * 0.3 - 0.4).to(DEV)      # shifted down: pooled maxima of both signs
+    x = torch.randn(1, K, R, generator=g).to(DEV)
+    gb = torch.randn(1, G, C, generator=g).to(DEV)
+    layer = mlp.WideLayer(W, s, t, False, mode)
+    out = torch.empty((1, C, R), device=DEV)
+    pool = torch.full((1, C, G), float("-inf"), device=DEV)
+    layer(x, out=out, relu_in=True, gbias=gb, gbias_rows=rows, out_pool=pool, pool_rows=rows)
+    acc = torch.einsum("ok,kr->or", W, torch.relu(x[0])) + gb[0].t().repeat_interleave(rows, dim=1)
+    ref = acc * s[:, None] + t[:, None]
+    tol = (2e-5 if mode == "x3" else 5e-3) * float(ref.abs().max())
+    assert float((out[0] - ref).abs().max()) <= tol
+    ref_pool = ref.view(C, G, rows).amax(-1)
+    assert float((pool[0] - ref_pool).abs().max()) <= tol and bool((ref_pool < 0).any()) and bool((ref_pool > 0).any())
+    # pooled-only call (no rows written), ReLU output
+    layer2 = mlp.WideLayer(W, s, t, True, mode)
+    pool2 = torch.full((1, C, G), float("-inf"), device=DEV)
+    layer2(x, out=None, out_pool=pool2, pool_rows=rows)
+    ref2 = torch.relu(torch.einsum("ok,kr->or", W, x[0]) * s[:, None] + t[:, None]).view(C, G, rows).amax(-1)
+    assert float((pool2[0] - ref2).abs().max()) <= tol
