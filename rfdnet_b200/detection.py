@@ -91,9 +91,12 @@ class _HeadFoldCache:
     precision = 'x3'  # 'x3' | 'fp16' | 'bf16': one tcgen05 chain kernel for the three convs; 'cuda': fp32 layer kernel
 
     def _heads(self):
-        if getattr(self, "_hf", None) is None:
+        ver = tuple(_mlp.state_version(m) for m in (self.conv1, self.bn1, self.conv2, self.bn2, self.conv3))
+        if getattr(self, "_hf", None) is None or getattr(self, "_hf_ver", None) != ver:   # also after in-place updates
+            self._drop_heads()
             self._hf = (_mlp.fold_conv_bn(self.conv1, self.bn1), _mlp.fold_conv_bn(self.conv2, self.bn2),
                         _mlp.fold_conv_bn(self.conv3, None))
+            self._hf_ver = ver
         return self._hf
 
     def _run_heads(self, x):

@@ -196,6 +196,13 @@ class WideLayer:
         return out
 
 
+def state_version(module):
+    """cheap fingerprint of a module's parameters and buffers: (data_ptr, in-place version counter) of each.  The folded /
+    packed weight caches of the inference paths are keyed on it, so an in-place update (optimizer step, manual edit) while
+    the module stays in eval mode is noticed on the next forward."""
+    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
 def check_f32(t, name):
     """Same precondition errors as the reference's CHECK_CUDA / CHECK_CONTIGUOUS / CHECK_IS_FLOAT (utils.h:5-25): the
     raw-pointer entry points must never reinterpret a half / double / CPU / strided tensor as dense fp32."""

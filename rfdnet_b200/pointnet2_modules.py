@@ -28,13 +28,16 @@ def build_shared_mlp(mlp_spec: List[int], bn: bool = True):
 
 
 class _FoldCache:
-    """Lazily folded (W, scale, shift, relu) per layer; dropped on train()/eval(), load_state_dict() and .to()/.cuda().
-    Parameters modified IN PLACE while the module stays in eval mode (e.g. an optimizer step without a mode switch)
-    are not noticed: call `module.eval()` again (or `_drop()`) after such an update."""
+    """Lazily folded (W, scale, shift, relu) per layer and the packed tensor-core image built from them; rebuilt whenever
+    a parameter or buffer of the MLP changes (mode switch, load_state_dict, .to(), or an in-place update: the cache is
+    keyed on the tensors' version counters)."""
 
     def _folded(self, seq):
-        if getattr(self, "_fold", None) is None:
+        ver = _mlp.state_version(seq)
+        if getattr(self, "_fold", None) is None or getattr(self, "_fold_ver", None) != ver:
+            self._drop()
             self._fold = _mlp.fold_sequential(seq)
+            self._fold_ver = ver
         return self._fold
 
     def _drop(self):

@@ -380,3 +380,25 @@ def test_chain_ex_relu_in_group_bias_and_epilogue_pool(mode):
     layer2(x, out=None, out_pool=pool2, pool_rows=rows)
     ref2 = torch.relu(torch.einsum("ok,kr->or", W, x[0]) * s[:, None] + t[:, None]).view(C, G, rows).amax(-1)
     assert float((pool2[0] - ref2).abs().max()) <= tol
+
+
+def test_inplace_weight_update_in_eval_mode_is_noticed():
+    """The folded / packed weight caches are keyed on the tensors' version counters: an in-place update
+    while the module stays in eval() must change the fused path's output exactly like a freshly built module."""
+    sa = pointnet2_modules.PointnetSAModuleVotes(npoint=128, radius=0.3, nsample=16, mlp=[5, 32, 32, 64], use_xyz=True,
+                                                 normalize_xyz=True).eval()
+    seeded_fill(sa, 11)
+    sa = sa.to(DEV)
+    xyz = torch.from_numpy(uniform_cloud(2, 1024, seed=5)).to(DEV)
+    feats = torch.randn(2, 5, 1024, generator=torch.Generator().manual_seed(3)).to(DEV)
+    with torch.no_grad():
+        _, f0, _ = sa(xyz, feats)
+        sa.mlp_module[0].weight.mul_(1.5)
+        sa.mlp_module[1].running_mean.add_(0.1)
+        _, f1, _ = sa(xyz, feats)
+    fresh = pointnet2_modules.PointnetSAModuleVotes(npoint=128, radius=0.3, nsample=16, mlp=[5, 32, 32, 64], use_xyz=True,
+                                                    normalize_xyz=True).eval().to(DEV)
+    fresh.load_state_dict(sa.state_dict())
+    with torch.no_grad():
+        _, f2, _ = fresh(xyz, feats)
+    assert not torch.equal(f0, f1) and torch.equal(f1, f2)

@@ -6,6 +6,7 @@ tag=${1:-r2}
 o=gpurun_out
 mkdir -p $o
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -15 > $o/${tag}_gputests.log
+timeout 600 python __graft_entry__.py smoke 2>&1 | tail -3 > $o/${tag}_smoke.log; cat $o/${tag}_smoke.log
 tail -3 $o/${tag}_gputests.log
 timeout 900 python bench.py --steps 5 --warmup 3 > $o/${tag}_bench.json 2> $o/${tag}_bench.err
 tail -c 400 $o/${tag}_bench.json
