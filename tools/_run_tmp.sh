@@ -1,7 +1,7 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_modules.py -m gpu -x -q -k "chain_ex" 2>&1 | tail -6
-timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_modules.py -x -q -k "chain_ex or stn_group_vs_reference" > gpurun_out/r3a_memcheck.log 2>&1
-tail -3 gpurun_out/r3a_memcheck.log; grep -c "Invalid\|out of bounds\|Misaligned" gpurun_out/r3a_memcheck.log
-timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_mesh.py -x -q -k "small_and_odd" > gpurun_out/r3a_racecheck.log 2>&1
-tail -3 gpurun_out/r3a_racecheck.log
+RFD_ONET_WAKE=1 timeout 900 python -m pytest tests/test_gpu_decoder.py -m gpu -x -q 2>&1 | tail -4
+for rep in 1 2 3; do for s in 0 1; do
+RFD_ONET_WAKE=$s timeout 300 python tools/prof_decoder.py 256 5 fp16 2 2>&1 | grep decode | sed "s/^/wake=$s /"
+RFD_ONET_WAKE=$s timeout 300 python tools/prof_decoder.py 1024 3 fp16 2 2>&1 | grep decode | sed "s/^/wake=$s /"
+done; done 2>&1 | grep -v "^+" | tee gpurun_out/r3c_wake_ab.log
