@@ -289,6 +289,13 @@ def run_gpu(args, rank, world, local):
         import traceback
         traceback.print_exc(file=sys.stderr)
         skip = {"error": repr(e)[:300]}
+    fullgen = None
+    try:
+        fullgen = full_generation_bench(dev, dev_sets[0][0])
+    except Exception as e:
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        fullgen = {"error": repr(e)[:300]}
 
     # ---- CPU baseline (bounded sample, rank 0, N = 1 only)
     cpu = None
@@ -350,6 +357,7 @@ def run_gpu(args, rank, world, local):
         "clocks": clocks,
         "train": train,
         "skip_propagation": skip,
+        "full_generation": fullgen,
     }
     return line
 
@@ -469,6 +477,39 @@ def skip_propagation_bench(dev, pc, ep):
     del sp
     torch.cuda.empty_cache()
     return out
+
+
+def full_generation_bench(dev, pc, scenes=2):
+    """ISCNet.generate's device part (network.py:56-153) for all 256 proposals of `scenes` scenes: detection ->
+    SkipPropagation (shape codes) -> ONet decoder on 32^3 -> meshes, everything on this library (pipeline.SceneGeneration).
+    NOT the headline metric (BASELINE's path takes the codes as given): it shows what the widened path costs."""
+    from rfdnet_b200.pipeline import SceneGeneration
+    from rfdnet_b200.synth import seeded_fill
+    net = SceneGeneration().eval()
+    seeded_fill(net, 29)
+    net = net.to(dev)
+    x = pc[:scenes].contiguous()
+    out = net(x, meshes=False)
+    with torch.no_grad():   # centre the seeded decoder's logits so that the surfaces are not empty
+        net.completion.decoder.fc_out.bias -= out["logits"].median()
+    for _ in range(2):
+        out = net(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        out = net(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    v, t, r = out["meshes"].to_host()
+    res = {"scenes": scenes, "proposals_per_scene": 256, "ms_per_scene": ms / scenes, "scenes_per_s": scenes / (ms * 1e-3),
+           "vertices": int(len(v)), "triangles": int(len(t)),
+           "stages": "detection + SkipPropagation.generate (STN_Group, PointSeg, ResnetPointnet on tcgen05) + decoder fp16 + "
+                     "rfd_extract_mesh; proposal selection (NMS) is the caller's"}
+    del net, out
+    torch.cuda.empty_cache()
+    return res
 
 
 def graph_time(fn, iters, reps=3):

@@ -6,10 +6,12 @@ One call = one pass over a batch of scenes of the path BASELINE.json's metric is
 The per-proposal shape code `c` (512-d) is produced in the reference by SkipPropagation, which is outside this
 path; callers pass it in (the benchmark uses seeded N(0,1) codes).
 """
+import math
+
 import torch
 import torch.nn as nn
 
-from . import detection, generator, onet
+from . import completion, detection, generator, onet
 
 
 class GraphedDetection:
@@ -205,3 +207,59 @@ class SceneHotPath(nn.Module):
                   "h_snap": torch.empty((64, 3), dtype=torch.int64).pin_memory()}
             self._mesh_pool_cache = mp
         return mp
+
+
+class SceneGeneration(nn.Module):
+    """The device part of ISCNet.generate (models/iscnet/modules/network.py:56-153), end to end on this library:
+
+        detection (backbone -> votes -> 256 proposals, proposal features exported)          network.py:66-83
+        -> box centres + heading angles of the kept proposals                                network.py:109-119
+        -> SkipPropagation.generate: per-proposal shape codes                                network.py:124, skip_propagation.py:84-129
+        -> ONet decoder on the dense R^3 lattice, z = prior mean                             generator.py:64-97, occupancy_net.py:147-175
+        -> meshes (pad, marching cubes, vertex transform)                                    generator.py:145-168
+
+    What the reference does in between on the HOST -- parse_predictions, 3D NMS and the ground-truth matching that pick
+    BATCH_PROPOSAL_IDs (network.py:84-101) -- is outside the hot path: callers pass the proposal ids to
+    keep (B, K) or get all proposals.  Sub-module names follow ISCNet's (`skip_propagation`, `completion.decoder`), the
+    detection part sits under `detection.*` as in SceneHotPath."""
+
+    def __init__(self, input_feature_dim=1, num_proposal=256, z_dim=32, c_dim=512, resolution=32, padding=0.1,
+                 num_heading_bin=12, precision='fp16'):
+        super().__init__()
+        self.detection = detection.DetectionHotPath(input_feature_dim, num_proposal, num_heading_bin=num_heading_bin)
+        self.skip_propagation = completion.SkipPropagation(input_feature_dim=input_feature_dim, c_dim=c_dim, hidden_dim=512)
+        self.completion = completion.ONet(z_dim=z_dim, c_dim=c_dim, precision=precision)
+        self.num_heading_bin, self.resolution, self.padding, self.z_dim = num_heading_bin, resolution, padding, z_dim
+        self._grid = None
+
+    @staticmethod
+    def heading_angles(end_points, num_heading_bin):
+        """scannet_config.py:55-63 (class2angle_cuda) on the arg-max heading bin + its residual (network.py:112-117)"""
+        cls = torch.argmax(end_points['heading_scores'], -1)
+        res = end_points['heading_residuals_normalized'] * (math.pi / num_heading_bin)
+        res = torch.gather(res, 2, cls.unsqueeze(-1)).squeeze(2)
+        angle = cls.float() * (2 * math.pi / num_heading_bin) + res
+        return angle - 2 * math.pi * (angle > math.pi).float()
+
+    @torch.no_grad()
+    def forward(self, point_clouds, proposal_ids=None, meshes=True):
+        """point_clouds (B,N,3+F) f32 cuda; proposal_ids (B,K) int64 or None (= all) ->
+        dict(end_points, codes (B*K, c_dim), logits (B*K, R^3), meshes: generator.MeshBatch | None)"""
+        ep, prop_feat = self.detection(point_clouds, export_proposal_feature=True)
+        centers, angles = ep['center'], self.heading_angles(ep, self.num_heading_bin)
+        if proposal_ids is not None:
+            ids = proposal_ids.long()
+            prop_feat = torch.gather(prop_feat, 2, ids.unsqueeze(1).expand(-1, prop_feat.shape[1], -1))
+            centers = torch.gather(centers, 1, ids.unsqueeze(-1).expand(-1, -1, 3))
+            angles = torch.gather(angles, 1, ids)
+        codes = self.skip_propagation.generate(centers.contiguous(), angles.contiguous(), prop_feat.contiguous(), point_clouds)
+        B, C, K = codes.shape
+        codes = codes.transpose(1, 2).contiguous().view(B * K, C)
+        dev = point_clouds.device
+        if self._grid is None or self._grid.device != dev:
+            self._grid = onet.make_3d_grid(self.resolution, 1 + self.padding, dev)
+        z = torch.zeros((B * K, self.z_dim), dtype=torch.float32, device=dev)            # prior mean (generator.py:79)
+        logits = self.completion.decoder.decode(self._grid, z, codes)
+        mb = generator.extract_meshes(logits, self.resolution, 0.5, self.padding, vertices_per_object=24576,
+                                      triangles_per_object=49152) if meshes else None
+        return {"end_points": ep, "codes": codes, "logits": logits, "meshes": mb}

@@ -169,3 +169,33 @@ def test_run_host_mesh_result_equals_logits_path():
     assert np.array_equal(np.unpackbits(bits.view(np.uint8), bitorder="little").reshape(256, -1).astype(bool), occ)
     with pytest.raises(RuntimeError, match="did not fit"):
         net.run_host(pc, codes, logits_host, torch.device(DEV), result="mesh", mesh_capacity=(8, 8))
+
+
+def test_scene_generation_pipeline_composes_the_pieces():
+    """pipeline.SceneGeneration = ISCNet.generate's device part (network.py:56-153): detection -> SkipPropagation ->
+    decoder -> meshes; equals the pieces called one by one, for all proposals and for a caller-chosen subset."""
+    from rfdnet_b200.pipeline import SceneGeneration
+    from rfdnet_b200.synth import scannet_like_batch
+    net = SceneGeneration().eval()
+    seeded_fill(net, 6)
+    net = net.to(DEV)
+    pc = torch.from_numpy(scannet_like_batch(1, 20000, seed0=21)).to(DEV)
+    ids = torch.tensor([[3, 200, 17, 255, 64, 9, 100, 31]], device=DEV)
+    out = net(pc, proposal_ids=ids)
+    assert out["codes"].shape == (8, 512) and out["logits"].shape == (8, 32768) and len(out["meshes"]) == 8
+    with torch.no_grad():
+        ep, pf = net.detection(pc, export_proposal_feature=True)
+        ang = SceneGeneration.heading_angles(ep, 12)
+        assert float(ang.max()) <= np.pi + 1e-6 and float(ang.min()) > -np.pi - 1e-6
+        codes = net.skip_propagation.generate(ep["center"][:, ids[0]].contiguous(), ang[:, ids[0]].contiguous(),
+                                              pf[:, :, ids[0]].contiguous(), pc)
+    assert torch.equal(out["codes"], codes.transpose(1, 2).reshape(8, 512))
+    lg = out["logits"].cpu().numpy().reshape(8, 32, 32, 32)
+    for b in (0, 7):
+        v_ref, t_ref, keys = cpu_ref.extract_mesh(lg[b])
+        order = np.argsort(keys, kind="stable")
+        v, t = out["meshes"].mesh(b)
+        assert np.array_equal(v, v_ref[order].astype(np.float32)) and len(t) == len(t_ref)
+    full = net(pc, meshes=False)
+    assert full["codes"].shape == (256, 512) and full["meshes"] is None and bool(torch.isfinite(full["logits"]).all())
+    assert torch.allclose(full["codes"][ids[0]], out["codes"], atol=1e-5)

@@ -1,7 +1,4 @@
 set -x
 mkdir -p gpurun_out
-RFD_ONET_WAKE=1 timeout 900 python -m pytest tests/test_gpu_decoder.py -m gpu -x -q 2>&1 | tail -4
-for rep in 1 2 3; do for s in 0 1; do
-RFD_ONET_WAKE=$s timeout 300 python tools/prof_decoder.py 256 5 fp16 2 2>&1 | grep decode | sed "s/^/wake=$s /"
-RFD_ONET_WAKE=$s timeout 300 python tools/prof_decoder.py 1024 3 fp16 2 2>&1 | grep decode | sed "s/^/wake=$s /"
-done; done 2>&1 | grep -v "^+" | tee gpurun_out/r3c_wake_ab.log
+timeout 900 python -m pytest tests/test_gpu_mesh.py tests/test_gpu_modules.py -m gpu -x -q -k "scene_generation or inplace_weight" 2>&1 | tail -8
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-train 2>gpurun_out/r3d_err.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value']); print(d['full_generation']); print(d['skip_propagation']['generate_ms'])" || tail -20 gpurun_out/r3d_err.log
