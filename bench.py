@@ -464,10 +464,14 @@ def skip_propagation_bench(dev, pc, ep):
 
     stn_ms, _ = timed(lambda: sp.stn(xyz, feats, box_xyz, heading))
     tot_ms, codes = timed(lambda: sp.generate(box_xyz, heading, box_feat, pc1), n=2)
+    sp.fast_precision = 'fp16'
+    fp16_ms, codes_h = timed(lambda: sp.generate(box_xyz, heading, box_feat, pc1), n=2)
     sp.fast_precision = None
     torch_ms, codes_t = timed(lambda: sp.generate(box_xyz, heading, box_feat, pc1), n=1)
     out = {"proposals": 256, "points": int(pc1.shape[1]), "nsample": 1024, "stn_group_ms": stn_ms, "generate_ms": tot_ms,
-           "generate_torch_layers_ms": torch_ms, "max_abs_diff_vs_torch_layers": float((codes - codes_t).abs().max()),
+           "generate_fp16_operands_ms": fp16_ms, "generate_torch_layers_ms": torch_ms,
+           "max_abs_diff_vs_torch_layers": float((codes - codes_t).abs().max()),
+           "max_abs_diff_fp16_vs_torch_layers": float((codes_h - codes_t).abs().max()),
            "codes_shape": list(codes.shape), "codes_finite": bool(torch.isfinite(codes).all()),
            "note": "generate_ms: STN_Group (rfd_query_and_group_rotated + 2 x rfd_mlp_chain + rfd_stn_apply) + PointSeg + "
                    "ResnetPointnet on the tcgen05 chain kernel (rfd_mlp_chain_ex, x3 = fp32-grade operands, 8.6 MFLOP per "
