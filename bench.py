@@ -28,6 +28,15 @@ WORKLOAD = "full hot path: 80k-pt scene -> backbone (4 SA + 2 FP) + vote + 256 p
 FLOP_PER_POINT = 1312768.0
 
 
+_T0 = time.perf_counter()
+
+
+def _mark(what):
+    """wall-clock trace of the bench's sections on stderr (the JSON line on stdout stays alone)"""
+    sys.stderr.write(f"[bench +{time.perf_counter() - _T0:7.1f}s] {what}\n")
+    sys.stderr.flush()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -207,6 +216,7 @@ def run_gpu(args, rank, world, local):
         pc, codes = dev_sets[i & 1]
         return net(pc, codes)
 
+    _mark("model + inputs built")
     # ---- warm-up
     for i in range(args.warmup):
         step_dev(i)
@@ -233,6 +243,7 @@ def run_gpu(args, rank, world, local):
     clocks = sampler.stop() if rank == 0 else None
     ms_max = D.max_over_ranks(ms, dev)
 
+    _mark("device-resident timed region done")
     # ---- timed region 2: end to end through the public API with host buffers.  The step's result is what
     # Generator3D returns to its caller -- the meshes (generator.py:145-168), extracted on the device -- plus the proposal
     # scores; the variant that ships every logit to the host (round 1's e2e) is timed as well.
@@ -256,6 +267,7 @@ def run_gpu(args, rank, world, local):
     t_e2e_lg, h2d_lg, d2h_lg = e2e_run("logits")
     t_e2e_b, h2d_b, d2h_b = e2e_run("bits")
 
+    _mark("end-to-end variants done")
     # ---- BASELINE config 5: training step with the NCCL gradient all-reduce (every rank takes part)
     train = None
     if not args.no_train:
@@ -279,7 +291,9 @@ def run_gpu(args, rank, world, local):
     fps = [s.elapsed_time(e) for n, s, e, w in timers if n == "fps"]
     value = world * S * args.steps / (ms_max * 1e-3)
     e2e = world * S * args.steps / t_e2e
+    _mark("train block done")
     qg = ballquery_group_bench(net, dev_sets[0][0], hbm)
+    _mark("ball query + group operator bench done")
     skip = None
     try:
         with torch.no_grad():
@@ -289,6 +303,7 @@ def run_gpu(args, rank, world, local):
         import traceback
         traceback.print_exc(file=sys.stderr)
         skip = {"error": repr(e)[:300]}
+    _mark("SkipPropagation block done")
     fullgen = None
     try:
         fullgen = full_generation_bench(dev, dev_sets[0][0])
@@ -297,6 +312,7 @@ def run_gpu(args, rank, world, local):
         traceback.print_exc(file=sys.stderr)
         fullgen = {"error": repr(e)[:300]}
 
+    _mark("full generation block done")
     # ---- CPU baseline (bounded sample, rank 0, N = 1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -314,6 +330,7 @@ def run_gpu(args, rank, world, local):
                "sample": cpu_sample_text(r), "objects_measured": r["objects_measured"],
                "extrapolated": r["extrapolated"], "measured_wall_s": r["wall_s"]}
 
+    _mark("cpu baseline done")
     traffic = traffic_src = None
     tp = os.path.join(ROOT, "profiles", "onet_decode_traffic.json")
     if os.path.exists(tp):
@@ -573,6 +590,13 @@ def ballquery_group_bench(net, pc, hbm_peak, iters=20):
         nbytes = B * (12 * N + 12 * M + 4 * C * N + 4 * (3 + C) * M * Sn)
         per[name] = {"us": ms * 1e3, "MB": nbytes / 1e6, "GB/s": nbytes / (ms * 1e-3) / 1e9,
                      "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak}
+        # the product path of the same layer: ball query (indices only) + ONE tcgen05 kernel that gathers through the
+        # indices, runs the shared MLP and max-pools -- the (B,3+C,M,S) grouped tensor is never written or read
+        inds = torch.arange(M, dtype=torch.int32, device=src.device).expand(B, M).contiguous()
+        with torch.no_grad():
+            fus = graph_time(lambda: mod._forward_fused(src, f, inds, q), 10)
+        per[name]["product_path"] = {"us_ball_query_plus_gather_mlp_max": fus * 1e3,
+                                     "grouped_tensor_MB_not_materialised": B * 4 * (3 + C) * M * Sn / 1e6}
         tot_b += nbytes
         tot_ms += ms
     gbs = tot_b / (tot_ms * 1e-3) / 1e9
