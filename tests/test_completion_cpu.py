@@ -94,3 +94,69 @@ def test_pointseg_matches_reference(gc):
 def test_skip_propagation_state_dict_keys(gc):
     sp = completion.SkipPropagation(input_feature_dim=1, c_dim=512, hidden_dim=512)
     assert keys(sp) == list(gc["keys_skip_propagation"])
+
+
+def test_fast_encoder_algebra_on_cpu(monkeypatch):
+    """completion_fast.encode restructures PointSeg / ResnetPointnet (per-cloud biases instead of repeated global
+    features, `shortcut(x) + fc_1(h)` as one layer over [x | h], epilogue max-pools, ReLU-on-load).  Here the tcgen05
+    layer classes are replaced by plain torch stand-ins with the same call contract, so the ALGEBRA is checked against the
+    torch mirror on the CPU in every round (the kernels themselves are checked on the GPU, tests/test_gpu_modules.py)."""
+    import torch
+    from rfdnet_b200 import completion, completion_fast, mlp
+    from rfdnet_b200.synth import seeded_fill
+
+    class Chain:   # contract of mlp.ChainMlp(layers, xyz=0, mode).dense(...)
+        def __init__(self, layers, xyz=0, mode='x3'):
+            self.layers, self.ok = layers, True
+            self.out_C = layers[-1][0].shape[0]
+            self.n0 = layers[0][0].shape[0]
+
+        def dense(self, x, pool=1, want_cm=True, want_pm=False, relu_in=False, gbias=None, gbias_rows=0, out_cm=None,
+                  out_pool=None, pool_rows=0):
+            h = torch.relu(x[0]) if relu_in else x[0]
+            for li, (W, s, t, relu) in enumerate(self.layers):
+                acc = W @ h
+                if li == 0 and gbias is not None:
+                    acc = acc + gbias[0, :, :W.shape[0]].t().repeat_interleave(gbias_rows, dim=1)
+                h = acc * s[:, None] + t[:, None]
+                if relu:
+                    h = torch.relu(h)
+            if out_pool is not None:
+                out_pool[0] = torch.maximum(out_pool[0], h.view(h.shape[0], -1, pool_rows).amax(-1))
+            if out_cm is not None:
+                out_cm[0] = h
+                return out_cm, None
+            return (h.unsqueeze(0) if want_cm else None), None
+
+    class Wide:    # contract of mlp.WideLayer
+        def __init__(self, W, scale, shift, relu, mode='x3', block=256):
+            self.c = Chain([(W, scale, shift, relu)])
+
+        def __call__(self, x, out=None, relu_in=False, gbias=None, gbias_rows=0, out_pool=None, pool_rows=0):
+            self.c.dense(x, relu_in=relu_in, gbias=gbias, gbias_rows=gbias_rows, out_cm=out, out_pool=out_pool,
+                         pool_rows=pool_rows, want_cm=False)
+            return out
+
+    monkeypatch.setattr(mlp, "ChainMlp", Chain)
+    monkeypatch.setattr(mlp, "WideLayer", Wide)
+    sp = completion.SkipPropagation(input_feature_dim=1, c_dim=64, hidden_dim=48).eval()
+    seeded_fill(sp, 5)
+    g = torch.Generator().manual_seed(1)
+    B, K, n = 2, 3, 128
+    xyz = torch.randn(B, 3, K, n, generator=g) * 0.4
+    feats = torch.cat([torch.randn(B, 1, K, n, generator=g), torch.zeros(B, 1, K, n)], dim=1)
+    box = torch.randn(B, 128, K, generator=g)
+    with torch.no_grad():
+        # balance the segmentation head so that the mask is neither empty nor full
+        pts = torch.cat([xyz, feats[:, :1]], dim=1).permute(0, 2, 3, 1).contiguous().view(B * K, n, -1)
+        seg, _ = sp.point_seg(pts.transpose(1, 2).contiguous())
+        lg = seg.view(-1, 2)
+        d = torch.sort(lg[:, 0] - lg[:, 1]).values            # threshold half way between the two middle points:
+        sp.point_seg.conv4.bias[1] += 0.5 * (d[len(d) // 2 - 1] + d[len(d) // 2])   # no point sits on the boundary
+        ref, seg_pred, _ = sp._encode(xyz, feats, box)
+        out, mask = completion_fast.encode(sp, xyz, feats, box, mode='x3')
+    mask_ref = torch.argmax(seg_pred.view(B * K, n, 2), dim=-1).bool()
+    assert 0.2 < float(mask_ref.float().mean()) < 0.8
+    assert torch.equal(mask, mask_ref)
+    assert out.shape == ref.shape == (B, 64, K)
+    assert float((out - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
