@@ -9,110 +9,66 @@ from torch.autograd import Function
 from . import _ext, _lib
 
 
-class FurthestPointSampling(Function):
-    """pointnet2_utils.py:34-65"""
+def _operator(name, ref_lines, forward, backward=None):
+    """A torch.autograd.Function named like the reference's (pointnet2_utils.py:<ref_lines>) around one `_ext` entry
+    point.  forward(ctx, *args) -> outputs; index-valued operators (backward=None) mark every output non-differentiable,
+    the others pass backward(ctx, *grads) -> input gradients, computed by the scatter-add kernels of the library."""
 
-    @staticmethod
-    def forward(ctx, xyz, npoint):
-        out = _ext.furthest_point_sampling(xyz, npoint)
-        ctx.mark_non_differentiable(out)
+    def fwd(ctx, *args):
+        out = forward(ctx, *args)
+        if backward is None:
+            ctx.mark_non_differentiable(*(out if isinstance(out, tuple) else (out,)))
         return out
 
-    @staticmethod
-    def backward(ctx, grad_out):
-        return ()
+    def bwd(ctx, *grads):
+        return () if backward is None else backward(ctx, *grads)
 
+    return type(name, (Function,), {"forward": staticmethod(fwd), "backward": staticmethod(bwd),
+                                    "__doc__": f"pointnet2_utils.py:{ref_lines}"})
+
+
+def _saving(op, *keep):
+    """forward that stashes the named positional inputs for the backward pass before calling `op`"""
+    def forward(ctx, *args):
+        ctx.save_for_backward(*(args[i] for i in keep))
+        return op(*args)
+    return forward
+
+
+def _three_nn(ctx, unknown, known):
+    dist2, idx = _ext.three_nn(unknown, known)
+    return torch.sqrt(dist2), idx                      # the reference returns distances, the kernel squared ones (:125)
+
+
+def _gather_grad(ctx, g):
+    idx, features = ctx.saved_tensors
+    return _ext.gather_points_grad(g.contiguous(), idx, features.size(2)), None
+
+
+def _group_grad(ctx, g):
+    idx, features = ctx.saved_tensors
+    return _ext.group_points_grad(g.contiguous(), idx, features.size(2)), torch.zeros_like(idx)
+
+
+def _interpolate_grad(ctx, g):
+    idx, weight, features = ctx.saved_tensors
+    return (_ext.three_interpolate_grad(g.contiguous(), idx, weight, features.size(2)), torch.zeros_like(idx),
+            torch.zeros_like(weight))
+
+
+FurthestPointSampling = _operator("FurthestPointSampling", "34-65", lambda ctx, xyz, npoint: _ext.furthest_point_sampling(xyz, npoint))
+GatherOperation = _operator("GatherOperation", "68-101", _saving(_ext.gather_points, 1, 0), _gather_grad)
+ThreeNN = _operator("ThreeNN", "104-136", _three_nn)
+ThreeInterpolate = _operator("ThreeInterpolate", "139-191", _saving(_ext.three_interpolate, 1, 2, 0), _interpolate_grad)
+GroupingOperation = _operator("GroupingOperation", "194-240", _saving(_ext.group_points, 1, 0), _group_grad)
+# the Python-side argument order of the reference is (radius, nsample, xyz, new_xyz); the extension takes new_xyz first
+BallQuery = _operator("BallQuery", "243-276", lambda ctx, radius, nsample, xyz, new_xyz: _ext.ball_query(new_xyz, xyz, radius, nsample))
 
 furthest_point_sample = FurthestPointSampling.apply
-
-
-class GatherOperation(Function):
-    """pointnet2_utils.py:68-101"""
-
-    @staticmethod
-    def forward(ctx, features, idx):
-        ctx.save_for_backward(idx, features)
-        return _ext.gather_points(features, idx)
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        idx, features = ctx.saved_tensors
-        N = features.size(2)
-        return _ext.gather_points_grad(grad_out.contiguous(), idx, N), None
-
-
 gather_operation = GatherOperation.apply
-
-
-class ThreeNN(Function):
-    """pointnet2_utils.py:104-136 (returns sqrt of the squared distances, :125)"""
-
-    @staticmethod
-    def forward(ctx, unknown, known):
-        dist2, idx = _ext.three_nn(unknown, known)
-        dist = torch.sqrt(dist2)
-        ctx.mark_non_differentiable(dist, idx)
-        return dist, idx
-
-    @staticmethod
-    def backward(ctx, grad_dist, grad_idx):
-        return ()
-
-
 three_nn = ThreeNN.apply
-
-
-class ThreeInterpolate(Function):
-    """pointnet2_utils.py:139-191"""
-
-    @staticmethod
-    def forward(ctx, features, idx, weight):
-        ctx.save_for_backward(idx, weight, features)
-        return _ext.three_interpolate(features, idx, weight)
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        idx, weight, features = ctx.saved_tensors
-        m = features.size(2)
-        grad_features = _ext.three_interpolate_grad(grad_out.contiguous(), idx, weight, m)
-        return grad_features, torch.zeros_like(idx), torch.zeros_like(weight)
-
-
 three_interpolate = ThreeInterpolate.apply
-
-
-class GroupingOperation(Function):
-    """pointnet2_utils.py:194-240"""
-
-    @staticmethod
-    def forward(ctx, features, idx):
-        ctx.save_for_backward(idx, features)
-        return _ext.group_points(features, idx)
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        idx, features = ctx.saved_tensors
-        N = features.size(2)
-        return _ext.group_points_grad(grad_out.contiguous(), idx, N), torch.zeros_like(idx)
-
-
 grouping_operation = GroupingOperation.apply
-
-
-class BallQuery(Function):
-    """pointnet2_utils.py:243-276 -- note the Python-side order (radius, nsample, xyz, new_xyz)."""
-
-    @staticmethod
-    def forward(ctx, radius, nsample, xyz, new_xyz):
-        output = _ext.ball_query(new_xyz, xyz, radius, nsample)
-        ctx.mark_non_differentiable(output)
-        return output
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        return ()
-
-
 ball_query = BallQuery.apply
 
 
