@@ -59,7 +59,7 @@ for tf32 in (True, False):
     t = wall(ref_batched, 1)
     print(f"reference op sequence, 16 objects per call, on device,  tf32={tf32}: {t * 1e3:.1f} ms")
 t = wall(ours, 3)
-print(f"rfdnet_b200 decode (one call, bf16 tcgen05) + .cpu(): {t * 1e3:.1f} ms")
+print(f"rfdnet_b200 decode (one call, default tcgen05 mode) + .cpu(): {t * 1e3:.1f} ms")
 a = torch.cat([x.view(1, -1) for x in ref_loop()[:8]]).to(dev)
 b = dec.decode(grid, z[:8], c[:8])
 print(f"max |logit difference| vs the fp32 reference sequence on 8 objects: {float((a - b).abs().max()):.3e} (scale {float(a.abs().max()):.2f})")
