@@ -94,3 +94,19 @@ def test_equal_values_and_threshold_ties():
     occ[1, 1, 1] = np.nextafter(np.float32(0), np.float32(1))
     v, t, _ = cpu_ref.extract_mesh(occ)
     assert len(v) == 6 and len(t) == 8
+
+
+def test_oracle_matches_committed_golden_meshes():
+    """tests/golden/golden_mesh.npz (made by tests/golden/make_golden_mesh.py) pins the oracle restatement itself."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_mesh", os.path.join(ROOT, "tests", "golden", "make_golden_mesh.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "golden_mesh.npz"))
+    for name, f in mg.fields().items():
+        for thr, pad in ((0.5, 0.1), (0.3, 0.25)):
+            d = mg.digest(*cpu_ref.extract_mesh(f, thr, pad))
+            assert d["nv"] > 0
+            for k, val in d.items():
+                g = gold[f"{name}_{thr}_{pad}_{k}"]
+                assert np.array_equal(np.asarray(val), g), (name, thr, pad, k)
