@@ -165,6 +165,13 @@ int rfd_mlp_chain(int mode, const float *x, int B, int K0, int L, const void *pa
 int rfd_mlp_chain_ex(int mode, const float *x, int B, int K0, int L, const void *packed, int C1, int C2, int C3,
                      int relu_last, int pool, float *out_cm, float *out_pm, int relu_in, const float *gbias,
                      int gbias_rows, float *out_pool, int pool_rows, void *stream);
+/* the same options on ROW-MAJOR operands: x_pm (B, L, ldi) f32, the K0 input channels in columns [0, K0) of every row (ldi a
+ * multiple of 4, base 16-byte aligned); out_pm (B, L, ldo) receives the C_last outputs in columns [out_col0, out_col0 +
+ * C_last) (or NULL); out_pool (B, L/pool_rows, C_last).  A tile reads 128 contiguous rows -- sequential HBM access where the
+ * channel-major form touches one DRAM page per channel -- and channel concatenation is a column offset into a wider row. */
+int rfd_mlp_chain_rows(int mode, const float *x_pm, int ldi, int B, int K0, int L, const void *packed, int C1, int C2, int C3,
+                       int relu_last, float *out_pm, int ldo, int out_col0, int relu_in, const float *gbias,
+                       int gbias_rows, float *out_pool, int pool_rows, void *stream);
 int rfd_sa_mlp_chain(int mode, const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx, int B, int N,
                      int M, int S, int C, float radius, int normalize_xyz, const void *packed, int C1, int C2, int C3,
                      float *out_cm, float *out_pm, void *stream);

@@ -41,6 +41,7 @@ SIGNATURES = {
     "rfd_mlp_chain_pack": [_i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp],
     "rfd_mlp_chain": [_i, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "rfd_mlp_chain_ex": [_i, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp],
+    "rfd_mlp_chain_rows": [_i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp],
     "rfd_sa_mlp_chain": [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _i, _i, _i, _vp, _vp, _vp],
     "rfd_transpose_features": [_vp, _i, _i, _i, _i, _vp, _vp],
     "rfd_onet_packed_bytes": [_i],

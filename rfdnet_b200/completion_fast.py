@@ -6,8 +6,9 @@ pointseg.py:7-168, layers.py:9-48,340-392.  For the 256 proposals of a scene the
 completion.py) fp32 cuDNN / cuBLAS calls with every activation through HBM and the PointNet "global feature" materialised
 as a repeated tensor (B*K, 1024, n) and concatenated.
 
-Here every pointwise layer is a launch of rfd_mlp_chain_ex over ALL rows at once (x kept channel-major (C, R), so channel
-concatenation is adjacency in one buffer), and the algebra removes what does not need computing:
+Here every pointwise layer is a launch of rfd_mlp_chain_rows over ALL rows at once (activations kept row-major (R, C): a
+tile reads 128 contiguous rows, channel concatenation is a column offset into a wider row), and the algebra removes what
+does not need computing:
   * a concatenated per-cloud constant (the max-pooled half of a PointNet concat) contributes W_b . pooled -- one value
     per (cloud, output channel): it enters layer 0 as a per-group bias (gbias), the repeated tensor is never built and
     the layer's K halves (1088 -> 64 for the segmentation head's first conv, 1024 -> 512 in the encoder blocks);
@@ -99,58 +100,47 @@ def _tnet_matrix(t, pooled, k):
     return x.view(-1, k, k)
 
 
-def _neg_inf(shape, dev):
-    return torch.full(shape, float("-inf"), dtype=torch.float32, device=dev)
-
-
 @torch.no_grad()
 def encode(sp, xyz, feats, box_feature, mode='x3'):
     """SkipPropagation._encode (eval): xyz (B,3,K,n) aligned coordinates, feats (B,C,K,n) (channel 0 = height),
-    box_feature (B,128,K) -> (codes (B,c_dim,K), mask (B*K,n) bool)."""
+    box_feature (B,128,K) -> (codes (B,c_dim,K), mask (B*K,n) bool).  All activations are row-major (1, R, C), R = B*K*n."""
     P = packed(sp, mode)
     B, _, K, n = xyz.shape
     BK, R, dev = B * K, B * K * n, xyz.device
     assert n % 128 == 0, "points per proposal must be a multiple of the 128-row tile"
     f = sp.point_seg.feat
 
-    def rows(t):   # (B,C,K,n) -> (1,C,R) channel-major over all rows
-        return t.permute(1, 0, 2, 3).reshape(1, t.shape[1], R).contiguous()
+    def rows(t):   # (B,C,K,n) -> (1,R,C): one row per point, clouds contiguous
+        return t.permute(0, 2, 3, 1).reshape(1, R, t.shape[1])
 
-    pts = torch.cat([rows(xyz), rows(feats[:, :1])], dim=1)                          # (1,4,R): xyz', height
+    pts = torch.cat([rows(xyz), rows(feats[:, :1])], dim=2).contiguous()             # (1,R,4): xyz', height
 
     def tnet_pooled(pk, x):
         c12, c3 = pk
-        h, _ = c12.dense(x)                                                         # (1,128,R)
-        pooled = _neg_inf((1, 1024, BK), dev)
-        c3(h, out=None, out_pool=pooled, pool_rows=n)                               # conv3 + bn + relu, max over the cloud
-        return pooled[0].t().contiguous()                                           # (BK,1024)
+        h = c12.rows(x)                                                              # (1,R,128)
+        return c3(h, out=None, pool_rows=n)[0]                                       # conv3 + bn + relu, max per cloud: (BK,1024)
 
     # ---- PointNetEncoder (pointseg.py:88-133)
     trans = _tnet_matrix(f.stn, tnet_pooled(P.stn, pts), 3)                          # (BK,3,3)
-    p3 = pts[0, :3].view(3, BK, n).permute(1, 2, 0)                                  # (BK,n,3)
-    p3 = torch.bmm(p3, trans)                                                        # only the coordinates are rotated
-    x = torch.cat([p3.permute(2, 0, 1).reshape(1, 3, R), pts[:, 3:]], dim=1).contiguous()
-    x64, _ = P.conv1.dense(x)                                                        # (1,64,R)
+    p3 = torch.bmm(pts[0, :, :3].reshape(BK, n, 3), trans)                           # only the coordinates are rotated
+    x = torch.cat([p3.reshape(1, R, 3), pts[:, :, 3:]], dim=2).contiguous()
+    x64 = P.conv1.rows(x)                                                            # (1,R,64)
     tfeat = _tnet_matrix(f.fstn, tnet_pooled(P.fstn, x64), 64)                       # (BK,64,64)
-    pf = torch.bmm(x64[0].view(64, BK, n).permute(1, 2, 0), tfeat)                   # (BK,n,64)
-    pointfeat = pf.permute(2, 0, 1).reshape(1, 64, R).contiguous()
-    x128, _ = P.conv2.dense(pointfeat)
-    g = _neg_inf((1, 1024, BK), dev)
-    P.conv3(x128, out=None, out_pool=g, pool_rows=n)                                 # bn3(conv3), max (values of either sign)
-    g = g[0].t().contiguous()                                                        # (BK,1024) global feature
+    pointfeat = torch.bmm(x64[0].view(BK, n, 64), tfeat).view(1, R, 64)
+    x128 = P.conv2.rows(pointfeat)
+    g = P.conv3(x128, out=None, pool_rows=n)[0]                                      # bn3(conv3), max (either sign): (BK,1024)
     # ---- segmentation head: conv1 over [global (repeated) | pointfeat] = per-cloud bias + 64-wide layer
     gb = (g @ P.seg_Wg.t()).view(1, BK, -1)                                          # (1,BK,512)
-    s1 = torch.empty((1, 512, R), dtype=torch.float32, device=dev)
+    s1 = torch.empty((1, R, 512), dtype=torch.float32, device=dev)
     P.seg1(pointfeat, out=s1, gbias=gb, gbias_rows=n)
-    logit, _ = P.seg234.dense(s1)                                                    # (1,2,R)
-    mask = (logit[0, 1] > logit[0, 0]).view(BK, n)                                   # argmax of log_softmax (ties -> class 0)
+    logit = P.seg234.rows(s1)                                                        # (1,R,2)
+    mask = (logit[0, :, 1] > logit[0, :, 0]).view(BK, n)                             # argmax of log_softmax (ties -> class 0)
     # ---- ResnetPointnet (layers.py:340-392) on mask * [xyz', height, box feature]
-    box = box_feature.permute(1, 0, 2).reshape(-1, BK)                               # (128,BK)
-    xin = torch.cat([pts[0], box.unsqueeze(-1).expand(-1, -1, n).reshape(-1, R)], dim=0)
-    xin = (xin * mask.view(1, R).to(xin.dtype)).unsqueeze(0).contiguous()            # (1,132,R)
+    box = box_feature.permute(0, 2, 1).reshape(BK, 1, -1).expand(-1, n, -1).reshape(1, R, -1)
+    xin = (torch.cat([pts, box], dim=2) * mask.view(1, R, 1).to(pts.dtype)).contiguous()     # (1,R,132)
     H = P.H
-    cur = torch.empty((1, 3 * H, R), dtype=torch.float32, device=dev)                # block 0: [net0 (2H) | h (H)]
-    P.fc_pos(xin, out=cur[:, :2 * H])
+    cur = torch.empty((1, R, 3 * H), dtype=torch.float32, device=dev)                # block 0 rows: [net0 (2H) | h (H)]
+    P.fc_pos(xin, out=cur, out_col0=0)
     pooled = None
     for i, (fc0, W0b, cat, Wsb) in enumerate(P.blocks):
         kin = 2 * H if i == 0 else H
@@ -158,12 +148,10 @@ def encode(sp, xyz, feats, box_feature, mode='x3'):
         if i > 0:
             rp = F.relu(pooled)                                                      # (BK,H): relu of the appended half
             gb0, gbs = (rp @ W0b.t()).view(1, BK, -1), (rp @ Wsb.t()).view(1, BK, -1)
-        fc0(cur[:, :kin], out=cur[:, kin:kin + H], relu_in=True, gbias=gb0, gbias_rows=n)
-        nxt = torch.empty((1, 2 * H, R), dtype=torch.float32, device=dev) if i < 4 else None
-        pl = _neg_inf((1, H, BK), dev)
-        cat(cur[:, :kin + H], out=None if nxt is None else nxt[:, :H], relu_in=True, gbias=gbs, gbias_rows=n,
-            out_pool=pl, pool_rows=n)
-        pooled = pl[0].t().contiguous()
+        # h = relu(fc_0(relu(x))) goes next to x in the same rows (columns [kin, kin + H)): the operand of `cat`
+        fc0(cur, out=cur, out_col0=kin, relu_in=True, gbias=gb0, gbias_rows=n)
+        nxt = torch.empty((1, R, 2 * H), dtype=torch.float32, device=dev) if i < 4 else None
+        pooled = cat(cur, out=nxt, out_col0=0, relu_in=True, gbias=gbs, gbias_rows=n, pool_rows=n)[0]
         cur = nxt
     codes = sp.encoder.fc_c(F.relu(pooled))                                          # (BK,c_dim)
     return codes.view(B, K, -1).transpose(1, 2), mask

@@ -104,6 +104,11 @@ struct ChainParams {
   int gbias_rows;         // rows per group (multiple of the 128-row tile)
   float *out_pool;        // (B, out_C, L / pool_rows): max over groups of rows of the (unpooled) output, caller-initialised
   int pool_rows;          //   to -inf; merged with a sign-aware atomic max (values of either sign)
+  // row-major ("point-major") dense mode (rfd_mlp_chain_rows): x_pm (B, L, ldi) with the K0 operand channels in columns
+  // [0, K0) of every row -- a tile reads 128 contiguous rows (sequential HBM access; the channel-major form reads 512 B per
+  // channel, one DRAM page each) -- out_pm rows have stride ldo and start at column out_col0; pool_pm: out_pool is (B, G, out_C)
+  const float *x_pm;
+  int ldi, ldo, out_col0, pool_pm;
 };
 
 // atomic max on a float of either sign (address initialised to -inf or any float)
@@ -314,6 +319,33 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
               chain_store_chunk<MODE>(a_base + kp * CH_PANEL + row * 128 + ((ch ^ (row & 7)) << 4), f);
             }
           }
+        } else if (P.x_pm) {
+          // dense row-major: lane = (row sub-index, 8-channel chunk); a warp instruction covers 4 rows x 64 channels (256 B each)
+          const int rsub = lane >> 3, ch = lane & 7;
+          const float *fb = P.x_pm + (size_t)b * P.L * P.ldi;
+#pragma unroll 1
+          for (int it = 0; it < 2; ++it) {
+            const int row = 4 * (we + 16 * it) + rsub;
+            const bool rv = (l0 + row) < P.L;
+            const float *src = fb + (size_t)(l0 + row) * P.ldi;
+            for (int kp = 0; kp < kpn; ++kp) {
+              const int c = (r * CH_APAN + kp) * 64 + ch * 8;
+              float f[8];
+              if (rv && c + 8 <= P.K0) {   // ldi and the base are multiples of 4 floats (checked on the host)
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(src + c));
+                const float4 d = __ldg(reinterpret_cast<const float4 *>(src + c + 4));
+                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = d.x; f[5] = d.y; f[6] = d.z; f[7] = d.w;
+              } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) f[u] = (rv && c + u < P.K0) ? __ldg(src + c + u) : 0.f;
+              }
+              if (P.relu_in) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], 0.f);
+              }
+              chain_store_chunk<MODE>(a_base + kp * CH_PANEL + row * 128 + ((ch ^ (row & 7)) << 4), f);
+            }
+          }
         } else {
           // dense channel-major: thread = (row, 8-channel chunk); a warp covers 32 consecutive rows of one chunk
           const int row = et & 127;
@@ -423,9 +455,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
                 }
                 const int col = cb + 8 * i + 2 * lc;
                 if (lr == 0 && m0v > -INFINITY) {
-                  float *o = P.out_pool + ((size_t)b * P.out_C + S.out_ch0 + col) * ngrp + grp;
-                  if (col < S.out_valid) atomic_max_float(o, m0v);
-                  if (col + 1 < S.out_valid) atomic_max_float(o + ngrp, m1v);
+                  if (P.pool_pm) {
+                    float *o = P.out_pool + ((size_t)b * ngrp + grp) * P.out_C + S.out_ch0 + col;
+                    if (col < S.out_valid) atomic_max_float(o, m0v);
+                    if (col + 1 < S.out_valid) atomic_max_float(o + 1, m1v);
+                  } else {
+                    float *o = P.out_pool + ((size_t)b * P.out_C + S.out_ch0 + col) * ngrp + grp;
+                    if (col < S.out_valid) atomic_max_float(o, m0v);
+                    if (col + 1 < S.out_valid) atomic_max_float(o + ngrp, m1v);
+                  }
                 }
               }
             }
@@ -444,7 +482,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
                   if (col + 1 < S.out_valid) o[P.L] = y1;
                 }
                 if (P.out_pm) {
-                  float *o = P.out_pm + ((size_t)b * P.L + row) * P.out_C + S.out_ch0 + col;
+                  float *o = P.out_pm + ((size_t)b * P.L + row) * P.ldo + P.out_col0 + S.out_ch0 + col;
                   if (col < S.out_valid) o[0] = y0;
                   if (col + 1 < S.out_valid) o[1] = y1;
                 }
@@ -690,6 +728,7 @@ static int chain_launch(int mode, ChainParams &P, const ChainPlan &p, const void
   P.shift = reinterpret_cast<const float *>(base + chain_off_shift(p));
   P.tab_floats = p.tab_floats;
   P.out_cm = out_cm; P.out_pm = out_pm; P.out_C = p.out_C;
+  if (P.ldo == 0) P.ldo = p.out_C;
   P.B = B; P.L = L; P.pool = pool;
   P.nsteps = p.nsteps;
   for (int s = 0; s < p.nsteps; ++s) {
@@ -741,6 +780,25 @@ extern "C" int rfd_mlp_chain_ex(int mode, const float *x, int B, int K0, int L, 
   P.x = x; P.K0 = K0; P.M = L / pool; P.S = pool;
   P.relu_in = relu_in; P.gbias = gbias; P.gbias_rows = gbias_rows; P.out_pool = out_pool; P.pool_rows = pool_rows;
   return chain_launch(mode, P, p, packed, relu_last, B, L, pool, out_cm, out_pm, stream);
+}
+
+extern "C" int rfd_mlp_chain_rows(int mode, const float *x_pm, int ldi, int B, int K0, int L, const void *packed, int C1, int C2,
+                                  int C3, int relu_last, float *out_pm, int ldo, int out_col0, int relu_in,
+                                  const float *gbias, int gbias_rows, float *out_pool, int pool_rows, void *stream) {
+  if (B < 0 || L < 0 || K0 < 1 || ldi < K0 || ldo < 0 || out_col0 < 0) return RFD_ERR_INVALID_ARGUMENT;
+  if (B == 0 || L == 0) return RFD_OK;
+  if (!x_pm || !packed || (!out_pm && !out_pool)) return RFD_ERR_INVALID_ARGUMENT;
+  if ((ldi & 3) || (reinterpret_cast<uintptr_t>(x_pm) & 15)) return RFD_ERR_INVALID_ARGUMENT;  // 16-byte row loads
+  if (gbias && (gbias_rows < CH_TILE_M || gbias_rows % CH_TILE_M || L % gbias_rows)) return RFD_ERR_UNSUPPORTED_SIZE;
+  if (out_pool && (pool_rows < CH_TILE_M || pool_rows % CH_TILE_M || L % pool_rows)) return RFD_ERR_UNSUPPORTED_SIZE;
+  const ChainPlan p = chain_plan(mode, K0, 0, C1, C2, C3);
+  if (!p.ok) return RFD_ERR_UNSUPPORTED_SIZE;
+  if (out_pm && ldo < out_col0 + p.out_C) return RFD_ERR_INVALID_ARGUMENT;
+  ChainParams P = {};
+  P.x_pm = x_pm; P.ldi = ldi; P.K0 = K0; P.M = L; P.S = 1;
+  P.ldo = out_pm ? ldo : p.out_C; P.out_col0 = out_col0; P.pool_pm = 1;
+  P.relu_in = relu_in; P.gbias = gbias; P.gbias_rows = gbias_rows; P.out_pool = out_pool; P.pool_rows = pool_rows;
+  return chain_launch(mode, P, p, packed, relu_last, B, L, 1, nullptr, out_pm, stream);
 }
 
 extern "C" int rfd_mlp_chain(int mode, const float *x, int B, int K0, int L, const void *packed, int C1, int C2, int C3,

@@ -146,6 +146,33 @@ class ChainMlp:
                                                     torch.cuda.current_stream().cuda_stream), "mlp_chain")
         return cm, pm
 
+    def rows(self, x, out=None, out_col0=0, want_out=True, relu_in=False, gbias=None, gbias_rows=0, out_pool=None, pool_rows=0):
+        """Row-major operands (rfd_mlp_chain_rows): x (B, L, ldi) f32, the K0 operand channels in columns [0, K0) of every
+        row -> out (B, L, ldo) columns [out_col0, out_col0 + C) (given, or a new (B, L, C) tensor; want_out=False: none);
+        gbias (B, L/gbias_rows, n0); out_pool (B, L/pool_rows, C), caller-initialised to -inf."""
+        check_f32(x, "x")
+        B, L, ldi = x.shape
+        assert ldi >= self.K0 and self.xyz == 0 and x.stride(1) == ldi, (x.shape, x.stride(), self.K0)
+        if out is None and want_out:
+            out = torch.empty((B, L, self.out_C), dtype=torch.float32, device=x.device)
+            out_col0 = 0
+        ldo = 0
+        if out is not None:
+            assert out.shape[:2] == (B, L) and out.stride(1) == out.shape[2] and out.dtype == torch.float32
+            ldo = out.shape[2]
+        if gbias is not None:
+            check_f32(gbias, "gbias")
+            assert gbias.shape == (B, L // gbias_rows, self.n0), (gbias.shape, self.n0)
+        if out_pool is not None:
+            assert out_pool.shape == (B, L // pool_rows, self.out_C) and out_pool.is_contiguous()
+        with torch.cuda.device(x.device), _lib.timed("mlp_chain_tc", B * L * self.flop_per_row):
+            _lib.check(_lib.load().rfd_mlp_chain_rows(self.mode, x.data_ptr(), ldi, B, self.K0, L, self.packed.data_ptr(),
+                                                      *self.C, self.relu_last, _ptr(out), ldo, int(out_col0),
+                                                      int(bool(relu_in)), _ptr(gbias), int(gbias_rows), _ptr(out_pool),
+                                                      int(pool_rows), torch.cuda.current_stream().cuda_stream),
+                       "mlp_chain_rows")
+        return out
+
     def gather(self, xyz, new_xyz, feat_pm, idx, radius, normalize_xyz, want_cm=True, want_pm=False):
         """Full SA fusion: rows gathered through idx (B,M,S) from xyz (B,N,3) / point-major features (B,N,C),
         centred on new_xyz, 3-layer MLP, max over S -> (out_cm (B,C3,M) | None, out_pm (B,M,C3) | None)."""
@@ -168,9 +195,10 @@ class ChainMlp:
 
 class WideLayer:
     """ONE pointwise layer of any input / output width on the tcgen05 chain kernel, for the PointNet-style encoders of
-    SkipPropagation (widths up to 1088 -> 1024): the output channels are split into blocks of <= 256, one single-layer
-    chain launch per block, every launch streaming the whole K through the resident A panels.  Rows of all clouds are one
-    batch: x (1, K, R) channel-major, so a block's output is the contiguous slice out[:, c0:c1, :]."""
+    SkipPropagation (widths up to 1536 -> 1024): the output channels are split into blocks of <= 256, one single-layer
+    chain launch per block, every launch streaming the whole K through the resident A panels.  Operands are ROW-major --
+    x (1, R, ld) with the K operand channels in the first K columns of every row -- so a tile reads 128 contiguous rows
+    and channel concatenation is a column offset into a wider row."""
 
     def __init__(self, W, scale, shift, relu, mode='x3', block=256):
         self.Cout, self.K = W.shape
@@ -182,18 +210,23 @@ class WideLayer:
             assert ch.ok, (W.shape, c0, c1)
             self.blocks.append((c0, c1, ch))
 
-    def __call__(self, x, out=None, relu_in=False, gbias=None, gbias_rows=0, out_pool=None, pool_rows=0):
-        """x (1,K,R) -> out (1,Cout,R) (given, or None = do not write the rows) ; gbias (1,G,Cout) ; out_pool (1,Cout,G')"""
-        assert x.shape[0] == 1 and x.shape[1] == self.K, (x.shape, self.K)
+    def __call__(self, x, out=None, out_col0=0, relu_in=False, gbias=None, gbias_rows=0, pool_rows=0):
+        """x (1,R,ld) -> out (1,R,ldo) columns [out_col0, out_col0 + Cout) (None = the rows are not written);
+        gbias (1,G,Cout) per-group bias; pool_rows > 0: also returns the max over groups of pool_rows rows, (1,G',Cout)."""
+        assert x.shape[0] == 1 and x.shape[2] >= self.K, (x.shape, self.K)
+        pooled = []
         for c0, c1, ch in self.blocks:
             gb = None
             if gbias is not None:
                 gb = torch.zeros((1, gbias.shape[1], ch.n0), dtype=torch.float32, device=x.device)
                 gb[:, :, :c1 - c0] = gbias[:, :, c0:c1]
-            ch.dense(x, want_cm=False, relu_in=relu_in, gbias=gb, gbias_rows=gbias_rows,
-                     out_cm=None if out is None else out[:, c0:c1, :],
-                     out_pool=None if out_pool is None else out_pool[:, c0:c1, :], pool_rows=pool_rows)
-        return out
+            pl = None
+            if pool_rows:
+                pl = torch.full((1, x.shape[1] // pool_rows, c1 - c0), float("-inf"), dtype=torch.float32, device=x.device)
+                pooled.append(pl)
+            ch.rows(x, out=out, out_col0=out_col0 + c0, want_out=False, relu_in=relu_in, gbias=gb, gbias_rows=gbias_rows,
+                    out_pool=pl, pool_rows=pool_rows)
+        return torch.cat(pooled, dim=2) if pool_rows else out
 
 
 def state_version(module):

@@ -105,37 +105,44 @@ def test_fast_encoder_algebra_on_cpu(monkeypatch):
     from rfdnet_b200 import completion, completion_fast, mlp
     from rfdnet_b200.synth import seeded_fill
 
-    class Chain:   # contract of mlp.ChainMlp(layers, xyz=0, mode).dense(...)
+    class Chain:   # contract of mlp.ChainMlp(layers, xyz=0, mode).rows(...)
         def __init__(self, layers, xyz=0, mode='x3'):
             self.layers, self.ok = layers, True
+            self.K0 = layers[0][0].shape[1]
             self.out_C = layers[-1][0].shape[0]
             self.n0 = layers[0][0].shape[0]
 
-        def dense(self, x, pool=1, want_cm=True, want_pm=False, relu_in=False, gbias=None, gbias_rows=0, out_cm=None,
-                  out_pool=None, pool_rows=0):
-            h = torch.relu(x[0]) if relu_in else x[0]
+        def rows(self, x, out=None, out_col0=0, want_out=True, relu_in=False, gbias=None, gbias_rows=0, out_pool=None,
+                 pool_rows=0):
+            h = x[0, :, :self.K0]
+            h = torch.relu(h) if relu_in else h
             for li, (W, s, t, relu) in enumerate(self.layers):
-                acc = W @ h
+                acc = h @ W.t()
                 if li == 0 and gbias is not None:
-                    acc = acc + gbias[0, :, :W.shape[0]].t().repeat_interleave(gbias_rows, dim=1)
-                h = acc * s[:, None] + t[:, None]
+                    acc = acc + gbias[0, :, :W.shape[0]].repeat_interleave(gbias_rows, dim=0)
+                h = acc * s[None, :] + t[None, :]
                 if relu:
                     h = torch.relu(h)
             if out_pool is not None:
-                out_pool[0] = torch.maximum(out_pool[0], h.view(h.shape[0], -1, pool_rows).amax(-1))
-            if out_cm is not None:
-                out_cm[0] = h
-                return out_cm, None
-            return (h.unsqueeze(0) if want_cm else None), None
+                out_pool[0] = torch.maximum(out_pool[0], h.view(-1, pool_rows, h.shape[1]).amax(1))
+            if out is None and want_out:
+                return h.unsqueeze(0).clone()
+            if out is not None:
+                out[0, :, out_col0:out_col0 + h.shape[1]] = h
+            return out
 
     class Wide:    # contract of mlp.WideLayer
         def __init__(self, W, scale, shift, relu, mode='x3', block=256):
             self.c = Chain([(W, scale, shift, relu)])
+            self.K, self.Cout = W.shape[1], W.shape[0]
 
-        def __call__(self, x, out=None, relu_in=False, gbias=None, gbias_rows=0, out_pool=None, pool_rows=0):
-            self.c.dense(x, relu_in=relu_in, gbias=gbias, gbias_rows=gbias_rows, out_cm=out, out_pool=out_pool,
-                         pool_rows=pool_rows, want_cm=False)
-            return out
+        def __call__(self, x, out=None, out_col0=0, relu_in=False, gbias=None, gbias_rows=0, pool_rows=0):
+            pl = None
+            if pool_rows:
+                pl = torch.full((1, x.shape[1] // pool_rows, self.Cout), float("-inf"))
+            self.c.rows(x, out=out, out_col0=out_col0, want_out=False, relu_in=relu_in, gbias=gbias, gbias_rows=gbias_rows,
+                        out_pool=pl, pool_rows=pool_rows)
+            return pl if pool_rows else out
 
     monkeypatch.setattr(mlp, "ChainMlp", Chain)
     monkeypatch.setattr(mlp, "WideLayer", Wide)

@@ -353,8 +353,9 @@ def test_detection_as_one_cuda_graph_equals_eager():
 
 @pytest.mark.parametrize("mode", ["x3", "fp16"])
 def test_chain_ex_relu_in_group_bias_and_epilogue_pool(mode):
-    """rfd_mlp_chain_ex: ReLU on the loaded operand, per-group pre-activation bias, and the max over groups of rows taken in
-    the epilogue (values of either sign), against plain torch; WideLayer splits a 600-wide output into column blocks."""
+    """rfd_mlp_chain_ex (channel-major) and rfd_mlp_chain_rows (row-major, WideLayer): ReLU on the loaded operand, per-group
+    pre-activation bias, and the max over groups of rows taken in the epilogue (values of either sign), against plain
+    torch; WideLayer splits a 600-wide output into column blocks and writes at a column offset of a wider row."""
     from rfdnet_b200 import mlp
     g = torch.Generator().manual_seed(12)
     K, C, R, rows = 200, 600, 3 * 256 + 128, 128          # 7 groups of 128 rows
@@ -362,24 +363,34 @@ def test_chain_ex_relu_in_group_bias_and_epilogue_pool(mode):
     W = (torch.randn(C, K, generator=g) / K ** 0.5).to(DEV)
     s = (torch.rand(C, generator=g) + 0.5).to(DEV)
     t = (torch.randn(C, generator=g) * 0.3 - 0.4).to(DEV)      # shifted down: pooled maxima of both signs
-    x = torch.randn(1, K, R, generator=g).to(DEV)
+    x = torch.randn(1, K, R, generator=g).to(DEV)             # channel-major
     gb = torch.randn(1, G, C, generator=g).to(DEV)
-    layer = mlp.WideLayer(W, s, t, False, mode)
-    out = torch.empty((1, C, R), device=DEV)
-    pool = torch.full((1, C, G), float("-inf"), device=DEV)
-    layer(x, out=out, relu_in=True, gbias=gb, gbias_rows=rows, out_pool=pool, pool_rows=rows)
     acc = torch.einsum("ok,kr->or", W, torch.relu(x[0])) + gb[0].t().repeat_interleave(rows, dim=1)
-    ref = acc * s[:, None] + t[:, None]
+    ref = acc * s[:, None] + t[:, None]                       # (C, R)
     tol = (2e-5 if mode == "x3" else 5e-3) * float(ref.abs().max())
-    assert float((out[0] - ref).abs().max()) <= tol
     ref_pool = ref.view(C, G, rows).amax(-1)
-    assert float((pool[0] - ref_pool).abs().max()) <= tol and bool((ref_pool < 0).any()) and bool((ref_pool > 0).any())
+    assert bool((ref_pool < 0).any()) and bool((ref_pool > 0).any())
+    # ---- channel-major entry, one 200-wide block of the layer
+    ch = mlp.ChainMlp([(W[:200].contiguous(), s[:200].contiguous(), t[:200].contiguous(), False)], xyz=0, mode=mode)
+    gbp = torch.zeros((1, G, ch.n0), device=DEV)
+    gbp[:, :, :200] = gb[:, :, :200]
+    pool = torch.full((1, 200, G), float("-inf"), device=DEV)
+    out_cm, _ = ch.dense(x, relu_in=True, gbias=gbp, gbias_rows=rows, out_pool=pool, pool_rows=rows)
+    assert float((out_cm[0] - ref[:200]).abs().max()) <= tol and float((pool[0] - ref_pool[:200]).abs().max()) <= tol
+    # ---- row-major entry through WideLayer: operand = first K columns of 208-wide rows, output at column 8 of 640-wide rows
+    xr = torch.full((1, R, 208), 7.0, device=DEV)
+    xr[0, :, :K] = x[0].t()
+    layer = mlp.WideLayer(W, s, t, False, mode)
+    out = torch.full((1, R, 640), -3.0, device=DEV)
+    pooled = layer(xr, out=out, out_col0=8, relu_in=True, gbias=gb, gbias_rows=rows, pool_rows=rows)
+    assert float((out[0, :, 8:8 + C] - ref.t()).abs().max()) <= tol
+    assert bool((out[0, :, :8] == -3.0).all()) and bool((out[0, :, 8 + C:] == -3.0).all())      # nothing else touched
+    assert pooled.shape == (1, G, C) and float((pooled[0] - ref_pool.t()).abs().max()) <= tol
     # pooled-only call (no rows written), ReLU output
     layer2 = mlp.WideLayer(W, s, t, True, mode)
-    pool2 = torch.full((1, C, G), float("-inf"), device=DEV)
-    layer2(x, out=None, out_pool=pool2, pool_rows=rows)
+    pooled2 = layer2(xr, out=None, pool_rows=rows)
     ref2 = torch.relu(torch.einsum("ok,kr->or", W, x[0]) * s[:, None] + t[:, None]).view(C, G, rows).amax(-1)
-    assert float((pool2[0] - ref2).abs().max()) <= tol
+    assert float((pooled2[0] - ref2.t()).abs().max()) <= tol
 
 
 def test_inplace_weight_update_in_eval_mode_is_noticed():
