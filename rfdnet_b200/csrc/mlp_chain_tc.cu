@@ -59,6 +59,8 @@ struct ChainBars {
   uint64_t w_empty[CH_NSLOT];
   uint64_t a_ready;      // 16 epilogue/loader warps: an A operand (round of layer 0, or a layer's output) is in place
   uint64_t a_free;       // MMA: the resident A panels of a layer-0 round have been consumed
+  uint64_t a_ready_pp[2];  // ping-pong rounds of a streamed layer-0 operand: one barrier per panel pair, so the loader (which
+                           // may run a full round ahead) can never advance a barrier two phases past the MMA thread's wait
   uint64_t acc_ready[2]; // MMA: accumulator of a step complete (ping-pong by step parity)
   uint32_t tmem_base;
 };
@@ -171,6 +173,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
     for (int i = 0; i < CH_NSLOT; ++i) { umma::mbar_init(&bars->w_full[i], 1); umma::mbar_init(&bars->w_empty[i], 1); }
     umma::mbar_init(&bars->a_ready, CH_EPI_WARPS);
     umma::mbar_init(&bars->a_free, 1);
+    umma::mbar_init(&bars->a_ready_pp[0], CH_EPI_WARPS);
+    umma::mbar_init(&bars->a_ready_pp[1], CH_EPI_WARPS);
     umma::mbar_init(&bars->acc_ready[0], 1);
     umma::mbar_init(&bars->acc_ready[1], 1);
     umma::fence_barrier_init();
@@ -186,7 +190,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
   const int tile_lo = (int)(((long long)P.num_tiles * blockIdx.x) / gridDim.x);
   const int tile_hi = (int)(((long long)P.num_tiles * (blockIdx.x + 1)) / gridDim.x);
   const int kp0 = P.st[0].kp;
-  const int rounds0 = kp0 == 0 ? 0 : (kp0 + CH_APAN - 1) / CH_APAN;
+  // layer-0 operand wider than the 4 resident panels: it streams through the panels in rounds.  Rounds are then 2 panels
+  // wide and alternate between panels {0,1} and {2,3} (hi; lo 4 panels above), so the loads + conversion of round r+1
+  // overlap the MMAs of round r (the first version used 4-panel rounds back to back: load, multiply, load, ...).
+  const bool pingpong = kp0 > CH_APAN;
+  const int RP = pingpong ? 2 : CH_APAN;
+  const int rounds0 = kp0 == 0 ? 0 : (kp0 + RP - 1) / RP;
 
   if (warp == 0) {
     // ---------------- producer: weight stages in consumption order: step, k panel, hi [, lo]
@@ -211,7 +220,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
     // ---------------- MMA issuer
     if (lane == 0) {
       const uint32_t a_addr = umma::smem_u32(s_a), w_addr = umma::smem_u32(s_w);
-      uint32_t st = 0, ph = 0, a_cnt = 0;
+      uint32_t st = 0, ph = 0, a_cnt = 0, pp_cnt[2] = {0u, 0u};
       for (int tile = tile_lo; tile < tile_hi; ++tile) {
         for (int s = 0; s < P.nsteps; ++s) {
           const ChainStep S = P.st[s];
@@ -221,11 +230,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
           const int rounds = s == 0 ? rounds0 : 1;
           uint32_t first = 1;
           for (int r = 0; r < rounds; ++r) {
-            if (!S.reuse_a) { umma::mbar_wait(&bars->a_ready, a_cnt & 1u); ++a_cnt; }
+            if (s == 0 && pingpong) { umma::mbar_wait(&bars->a_ready_pp[r & 1], pp_cnt[r & 1] & 1u); ++pp_cnt[r & 1]; }
+            else if (!S.reuse_a) { umma::mbar_wait(&bars->a_ready, a_cnt & 1u); ++a_cnt; }
             umma::tc_fence_after();
-            const int kpn = s == 0 ? min(CH_APAN, kp0 - r * CH_APAN) : S.kp;
+            const int kpn = s == 0 ? min(RP, kp0 - r * RP) : S.kp;
+            const int pb = (s == 0 && pingpong) ? (r & 1) * 2 : 0;
             for (int kp = 0; kp < kpn; ++kp) {
-              const uint32_t a_hi = a_addr + kp * CH_PANEL, a_lo = a_hi + CH_APAN * CH_PANEL;
+              const uint32_t a_hi = a_addr + (pb + kp) * CH_PANEL, a_lo = a_hi + CH_APAN * CH_PANEL;
               umma::mbar_wait(&bars->w_full[st], ph);
               umma::tc_fence_after();
               const uint32_t w_hi = w_addr + st * CH_SLOT;
@@ -252,7 +263,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
                 if (++st == CH_NSLOT) { st = 0; ph ^= 1u; }
               }
             }
-            if (s == 0 && r + 1 < rounds) umma::mma_commit(&bars->a_free);
+            if (s == 0 && r + (pingpong ? 2 : 1) < rounds) umma::mma_commit(&bars->a_free);  // a later round reuses these panels
           }
           umma::mma_commit(&bars->acc_ready[s & 1]);
         }
@@ -293,8 +304,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
       }
       // ---- layer-0 A operand, CH_APAN panels per round
       for (int r = 0; r < rounds0; ++r) {
-        if (r > 0) { umma::mbar_wait(&bars->a_free, free_cnt & 1u); ++free_cnt; }
-        const int kpn = min(CH_APAN, kp0 - r * CH_APAN);
+        if (r >= (pingpong ? 2 : 1)) { umma::mbar_wait(&bars->a_free, free_cnt & 1u); ++free_cnt; }
+        const int kpn = min(RP, kp0 - r * RP);
+        const int pb = pingpong ? (r & 1) * 2 : 0;
         if (P.idx) {
           // gather: lane = (row sub-index, 8-channel chunk); a warp instruction covers 4 rows x 64 channels (256 B each)
           const int rsub = lane >> 3, ch = lane & 7;
@@ -306,7 +318,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
             const int pk = rv ? __ldg(P.idx + (size_t)b * P.L + l0 + row) : 0;
             const float *src = fb + (size_t)pk * P.K0;
             for (int kp = 0; kp < kpn; ++kp) {
-              const int c = (r * CH_APAN + kp) * 64 + ch * 8;
+              const int c = (r * RP + kp) * 64 + ch * 8;
               float f[8];
               if (rv && c + 8 <= P.K0 && (P.K0 & 3) == 0) {
                 const float4 a = __ldg(reinterpret_cast<const float4 *>(src + c));
@@ -316,7 +328,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
 #pragma unroll
                 for (int u = 0; u < 8; ++u) f[u] = (rv && c + u < P.K0) ? __ldg(src + c + u) : 0.f;
               }
-              chain_store_chunk<MODE>(a_base + kp * CH_PANEL + row * 128 + ((ch ^ (row & 7)) << 4), f);
+              chain_store_chunk<MODE>(a_base + (pb + kp) * CH_PANEL + row * 128 + ((ch ^ (row & 7)) << 4), f);
             }
           }
         } else if (P.x_pm) {
@@ -329,7 +341,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
             const bool rv = (l0 + row) < P.L;
             const float *src = fb + (size_t)(l0 + row) * P.ldi;
             for (int kp = 0; kp < kpn; ++kp) {
-              const int c = (r * CH_APAN + kp) * 64 + ch * 8;
+              const int c = (r * RP + kp) * 64 + ch * 8;
               float f[8];
               if (rv && c + 8 <= P.K0) {   // ldi and the base are multiples of 4 floats (checked on the host)
                 const float4 a = __ldg(reinterpret_cast<const float4 *>(src + c));
@@ -343,7 +355,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
 #pragma unroll
                 for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], 0.f);
               }
-              chain_store_chunk<MODE>(a_base + kp * CH_PANEL + row * 128 + ((ch ^ (row & 7)) << 4), f);
+              chain_store_chunk<MODE>(a_base + (pb + kp) * CH_PANEL + row * 128 + ((ch ^ (row & 7)) << 4), f);
             }
           }
         } else {
@@ -355,17 +367,17 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
             float f[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              const int c = r * CH_APAN * 64 + c8 * 8 + u;
+              const int c = r * RP * 64 + c8 * 8 + u;
               f[u] = (rv && c < P.K0) ? __ldg(xb + (size_t)c * P.L) : 0.f;
               if (P.relu_in) f[u] = fmaxf(f[u], 0.f);
             }
-            chain_store_chunk<MODE>(a_base + (c8 >> 3) * CH_PANEL + row * 128 + (((c8 & 7) ^ (row & 7)) << 4), f);
+            chain_store_chunk<MODE>(a_base + (pb + (c8 >> 3)) * CH_PANEL + row * 128 + (((c8 & 7) ^ (row & 7)) << 4), f);
           }
         }
         umma::fence_proxy_async_smem();
         umma::tc_fence_before();
         __syncwarp();
-        if (lane == 0) umma::mbar_arrive(&bars->a_ready);
+        if (lane == 0) umma::mbar_arrive(pingpong ? &bars->a_ready_pp[r & 1] : &bars->a_ready);
       }
       if (P.has_xyz) asm volatile("bar.sync 1, %0;" ::"n"(32 * CH_EPI_WARPS) : "memory");  // s_rel visible to all epilogue warps
       (void)pk_row;
