@@ -182,7 +182,9 @@ int rfd_transpose_features(const float *features, int B, int C, int N, int Cp, f
  * rfd_query_and_group_rotated = rfd_query_and_group + the rotation of the relative coordinates about z by the box heading
  * (rot = [[cos, sin, 0], [-sin, cos, 0], [0, 0, 1]], :513-526), heading (B,M) radians, in the same kernel (RfD-Net:
  * radius 1.0, nsample 1024 over the whole cloud).  rfd_stn_apply = STN3d's last step (:455-462): theta (B,12,M) is the
- * regressed 3x4 matrix (row major, WITHOUT the identity, which the kernel adds), out = theta[:, :3] . g + theta[:, 3]. */
+ * regressed 3x4 matrix (row major, WITHOUT the identity, which the kernel adds), out = theta[:, :3] . g + theta[:, 3].
+ * With use_xyz the xyz channels inside new_features are rotated as well; the reference leaves those unrotated (only the
+ * returned grouped_xyz is rotated, :497-526) -- rfdnet_b200.stn_group.STN_Group restores them with a second call. */
 int rfd_query_and_group_rotated(const float *xyz, const float *new_xyz, const float *features, const float *heading,
                                 int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz,
                                 float *new_features, float *grouped_xyz, int *idx, void *stream);

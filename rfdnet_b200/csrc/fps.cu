@@ -22,6 +22,8 @@
 //     A thread here owns k = g, g+T, g+2T, ... (T = threads per cluster, a multiple of bs), i.e. one slot in
 //     ascending k -- so the in-register strict '>' scan is already rank-ordered;
 //   * "no candidate" (all points skipped) reproduces the reference result old = 0.
+#include <atomic>
+
 #include "common.cuh"
 #include <cmath>
 #include <cstdio>
@@ -448,15 +450,19 @@ extern "C" int rfd_furthest_point_sampling_cond(const float *xyz, int B, int N, 
     for (int c = cs; c >= 2 && c >= cs / 4; c /= 2) {
       const int p = (need + c - 1) / c;
       if (p > max_ppt) break;
-      static int cache[2][32][17];  // [threads==1024][ppt][cs] -> max active clusters + 1 (0 = unknown)
-      int &slot = cache[threads == 1024][p][c];
-      if (slot == 0) {
-        int maxc = 0;
-        rc = dispatch_fps(threads, p, xyz, B, N, m, bs_log2, Q, c, idx, new_xyz, nullptr, st, true, &maxc);
+      // [threads==1024][ppt][cs] -> max active clusters + 1 (0 = unknown); relaxed atomics: concurrent callers may both
+      // probe and store the same value
+      static std::atomic<int> cache[2][32][17];
+      std::atomic<int> &slot = cache[threads == 1024][p][c];
+      int known = slot.load(std::memory_order_relaxed);
+      if (known == 0) {
+        int probed = 0;
+        rc = dispatch_fps(threads, p, xyz, B, N, m, bs_log2, Q, c, idx, new_xyz, nullptr, st, true, &probed);
         if (rc != RFD_OK) return rc;
-        slot = maxc + 1;
+        known = probed + 1;
+        slot.store(known, std::memory_order_relaxed);
       }
-      const int maxc = slot - 1;
+      const int maxc = known - 1;
       if (getenv("RFD_FPS_DEBUG")) fprintf(stderr, "[rfd fps] candidate cluster=%d ppt=%d max active clusters=%d\n", c, p, maxc);
       if (maxc <= 0) continue;  // e.g. a 16-CTA (non-portable) cluster is not schedulable on this part
       const int waves = (B + maxc - 1) / maxc;

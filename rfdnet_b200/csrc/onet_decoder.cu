@@ -36,6 +36,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include <atomic>
+#include <mutex>
 #include <cstdlib>
 
 namespace rfd {
@@ -823,18 +824,23 @@ extern "C" int rfd_onet_decode_f32(const float *p, long long p_batch_stride, int
   cudaStream_t st = as_stream(stream);
   // unit scale / zero shift for the bias-free layers: one small constant buffer per device, created on first use
   static float *ones_zeros_dev[64] = {nullptr};
+  static std::mutex ones_zeros_mu;
   int cur_dev = 0;
   RFD_CHECK_CUDA(cudaGetDevice(&cur_dev), "decode_f32 getdevice");
   if (cur_dev < 0 || cur_dev >= 64) return RFD_ERR_UNSUPPORTED_SIZE;
-  if (!ones_zeros_dev[cur_dev]) {
-    float h[2 * DEC_H];
-    for (int i = 0; i < DEC_H; ++i) { h[i] = 1.f; h[DEC_H + i] = 0.f; }
-    float *d = nullptr;
-    RFD_CHECK_CUDA(cudaMalloc(&d, sizeof(h)), "decode_f32 malloc");
-    RFD_CHECK_CUDA(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice), "decode_f32 memcpy");
-    ones_zeros_dev[cur_dev] = d;
+  float *ones_zeros = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(ones_zeros_mu);
+    if (!ones_zeros_dev[cur_dev]) {
+      float h[2 * DEC_H];
+      for (int i = 0; i < DEC_H; ++i) { h[i] = 1.f; h[DEC_H + i] = 0.f; }
+      float *d = nullptr;
+      RFD_CHECK_CUDA(cudaMalloc(&d, sizeof(h)), "decode_f32 malloc");
+      RFD_CHECK_CUDA(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice), "decode_f32 memcpy");
+      ones_zeros_dev[cur_dev] = d;
+    }
+    ones_zeros = ones_zeros_dev[cur_dev];
   }
-  float *ones_zeros = ones_zeros_dev[cur_dev];
   for (int b0 = 0; b0 < B; b0 += (int)bc) {
     const int nb = (int)((B - b0) < bc ? (B - b0) : bc);
     float *x = workspace, *net = workspace + (size_t)bc * DEC_H * T;
