@@ -580,6 +580,291 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const Chain
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// wide_rows_kernel: ONE wide pointwise layer on row-major operands as a K-pipelined, role-split GEMM -- the shape the
+// encoders of SkipPropagation need (262 144 rows, K up to 1536, 137 GFLOP per layer), where the chain kernel above (built
+// for 0.5-4 GFLOP three-layer MLPs) loads, multiplies and stores a tile in sequence.
+//   warp 0      weight producer: 4-slot ring of 32-KB bulk copies (two K panels of split weights in flight)
+//   warp 1      MMA issuer: per 64-wide K panel 4 (fp16 / bf16) or 12 (x3) tcgen05.mma into one of TWO 256-column TMEM
+//               accumulators (tile parity)
+//   warps 2-9   loaders: fp32 rows -> (ReLU) -> 16-bit hi [+ lo] K-major swizzled A panel, 2-deep ring
+//   warps 10-17 epilogue: TMEM -> scale * (acc + group bias) + shift (+ ReLU) -> row-major output and / or the sign-aware
+//               max over row groups; it drains accumulator t while the loaders and the tensor pipe work on tile t + 1
+// Weights / tables: the packed buffer of a single-layer rfd_mlp_chain_pack (same stage order and table offsets).
+constexpr int WR_LOADERS = 16, WR_EPI = 8;
+constexpr int WR_THREADS = 32 * (2 + WR_LOADERS + WR_EPI);  // 832
+constexpr int WR_NSLOT = 4;
+constexpr int WR_SM_A = 0;                               // [hi b0][hi b1][lo b0][lo b1], 16 KB each
+constexpr int WR_SM_W = 4 * CH_PANEL;                    // 64 KB
+constexpr int WR_SM_TAB = WR_SM_W + WR_NSLOT * CH_SLOT;  // scale[256] shift[256]
+constexpr int WR_SM_BAR = WR_SM_TAB + 2 * 256 * 4;
+constexpr int WR_SMEM_BYTES = WR_SM_BAR + 256 + 1024;
+static_assert(WR_SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
+
+struct WideBars {
+  uint64_t w_full[WR_NSLOT], w_empty[WR_NSLOT];
+  uint64_t a_full[2], a_empty[2];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+struct WideParams {
+  const float *x;        // (R, ldi) row-major, operand = columns [0, K)
+  int ldi, K, kp, R;
+  const uint8_t *w;      // packed stages: per K panel hi [, lo] image of n x 128 B
+  const float *scale, *shift;
+  int n, n_valid, relu, relu_in;
+  const float *gbias;    // (R / gbias_rows, n) or nullptr
+  int gbias_rows;
+  float *out;            // (R, ldo) or nullptr; columns [out_col0, out_col0 + n_valid)
+  int ldo, out_col0;
+  float *out_pool;       // (R / pool_rows, n_valid) or nullptr
+  int pool_rows;
+  int num_tiles;
+};
+
+template <int MODE>
+__device__ __forceinline__ void wide_store_chunk(uint32_t dst, const float (&f)[8]) {
+  uint32_t h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    h[i] = MODE == CH_MODE_BF16 ? umma::pack_bf16x2(f[2 * i], f[2 * i + 1]) : umma::pack_f16x2(f[2 * i], f[2 * i + 1]);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+  if (MODE == CH_MODE_F16X3) {
+    uint32_t l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 hf = umma::unpack_f16x2(h[i]);
+      l[i] = umma::pack_f16x2(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 2 * CH_PANEL), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3])
+                 : "memory");
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(WR_THREADS, 1) wide_rows_kernel(const WideParams P) {
+  constexpr bool X3 = MODE == CH_MODE_F16X3;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *s_a = smem + WR_SM_A, *s_w = smem + WR_SM_W;
+  float *s_scale = reinterpret_cast<float *>(smem + WR_SM_TAB), *s_shift = s_scale + 256;
+  WideBars *bars = reinterpret_cast<WideBars *>(smem + WR_SM_BAR);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int i = 0; i < WR_NSLOT; ++i) { umma::mbar_init(&bars->w_full[i], 1); umma::mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(&bars->a_full[i], WR_LOADERS);
+      umma::mbar_init(&bars->a_empty[i], 1);
+      umma::mbar_init(&bars->acc_full[i], 1);
+      umma::mbar_init(&bars->acc_empty[i], WR_EPI);
+    }
+    umma::fence_barrier_init();
+  }
+  if (warp == 1) umma::tmem_alloc(&bars->tmem_base, 512);
+  for (int e = tid; e < 256; e += WR_THREADS) {
+    s_scale[e] = e < P.n ? __ldg(P.scale + e) : 0.f;
+    s_shift[e] = e < P.n ? __ldg(P.shift + e) : 0.f;
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int tile_lo = (int)(((long long)P.num_tiles * blockIdx.x) / gridDim.x);
+  const int tile_hi = (int)(((long long)P.num_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const uint32_t stage_bytes = (uint32_t)P.n * 128u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      for (int tile = tile_lo; tile < tile_hi; ++tile) {
+        size_t off = 0;
+        for (int i = 0; i < P.kp * (X3 ? 2 : 1); ++i) {
+          umma::mbar_wait(&bars->w_empty[st], ph ^ 1u);
+          umma::mbar_arrive_expect_tx(&bars->w_full[st], stage_bytes);
+          umma::bulk_g2s(s_w + st * CH_SLOT, P.w + off, stage_bytes, &bars->w_full[st]);
+          off += stage_bytes;
+          if (++st == WR_NSLOT) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t a_addr = umma::smem_u32(s_a), w_addr = umma::smem_u32(s_w);
+      const uint32_t idesc = MODE == CH_MODE_BF16 ? umma::make_idesc_bf16_f32(CH_TILE_M, (uint32_t)P.n)
+                                                  : umma::make_idesc_f16_f32(CH_TILE_M, (uint32_t)P.n);
+      uint32_t st = 0, ph = 0, g = 0, t = 0;
+      for (int tile = tile_lo; tile < tile_hi; ++tile, ++t) {
+        const uint32_t acc = t & 1u;
+        if (t >= 2) umma::mbar_wait(&bars->acc_empty[acc], ((t >> 1) - 1u) & 1u);  // the epilogue drained this accumulator
+        umma::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256u;
+        for (int kp = 0; kp < P.kp; ++kp, ++g) {
+          const uint32_t b = g & 1u;
+          umma::mbar_wait(&bars->a_full[b], (g >> 1) & 1u);
+          umma::tc_fence_after();
+          const uint32_t a_hi = a_addr + b * CH_PANEL, a_lo = a_hi + 2 * CH_PANEL;
+          umma::mbar_wait(&bars->w_full[st], ph);
+          umma::tc_fence_after();
+          const uint32_t w_hi = w_addr + st * CH_SLOT;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma::mma_f16_ss(d_tmem, umma::make_desc_k_sw128(a_hi + k * 32), umma::make_desc_k_sw128(w_hi + k * 32), idesc,
+                             (kp | k) ? 1u : 0u);
+            if (X3)
+              umma::mma_f16_ss(d_tmem, umma::make_desc_k_sw128(a_lo + k * 32), umma::make_desc_k_sw128(w_hi + k * 32), idesc, 1u);
+          }
+          umma::mma_commit(&bars->w_empty[st]);
+          if (++st == WR_NSLOT) { st = 0; ph ^= 1u; }
+          if (X3) {
+            umma::mbar_wait(&bars->w_full[st], ph);
+            umma::tc_fence_after();
+            const uint32_t w_lo = w_addr + st * CH_SLOT;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma::mma_f16_ss(d_tmem, umma::make_desc_k_sw128(a_hi + k * 32), umma::make_desc_k_sw128(w_lo + k * 32), idesc, 1u);
+            umma::mma_commit(&bars->w_empty[st]);
+            if (++st == WR_NSLOT) { st = 0; ph ^= 1u; }
+          }
+          umma::mma_commit(&bars->a_empty[b]);
+        }
+        umma::mma_commit(&bars->acc_full[acc]);
+      }
+    }
+  } else if (warp < 2 + WR_LOADERS) {
+    // ---------------- loaders: lane = (row sub-index, 8-channel chunk); a warp instruction covers 4 rows x 64 channels
+    const int wl = warp - 2, rsub = lane >> 3, ch = lane & 7;
+    const uint32_t a_base = umma::smem_u32(s_a);
+    constexpr int NIT = CH_TILE_M / (4 * WR_LOADERS);   // row groups per warp and panel (2)
+    // software pipeline: the global loads of panel g + 1 are issued before panel g is converted and stored, so (with the
+    // two-deep smem ring) up to three panels of a row tile are in flight per CTA -- the A operand comes from HBM at the
+    // latency of a full memory round trip per panel otherwise
+    float cur[NIT][8], nxt[NIT][8];
+    auto fetch = [&](int tile, int kp, float (&f)[NIT][8]) {
+      const long long l0 = (long long)tile * CH_TILE_M;
+      const int c = kp * 64 + ch * 8;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int row = 4 * (wl + WR_LOADERS * it) + rsub;
+        const bool rv = l0 + row < P.R;
+        const float *src = P.x + (size_t)(l0 + row) * P.ldi;
+        if (rv && c + 8 <= P.K) {
+          const float4 a = __ldg(reinterpret_cast<const float4 *>(src + c));
+          const float4 d = __ldg(reinterpret_cast<const float4 *>(src + c + 4));
+          f[it][0] = a.x; f[it][1] = a.y; f[it][2] = a.z; f[it][3] = a.w; f[it][4] = d.x; f[it][5] = d.y; f[it][6] = d.z; f[it][7] = d.w;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) f[it][u] = (rv && c + u < P.K) ? __ldg(src + c + u) : 0.f;
+        }
+      }
+    };
+    uint32_t g = 0;
+    if (tile_lo < tile_hi) fetch(tile_lo, 0, cur);
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+      for (int kp = 0; kp < P.kp; ++kp, ++g) {
+        const uint32_t b = g & 1u;
+        // next panel (of this tile, or the first of the next tile)
+        const bool last_kp = kp + 1 == P.kp;
+        const int ntile = last_kp ? tile + 1 : tile, nkp = last_kp ? 0 : kp + 1;
+        if (ntile < tile_hi) fetch(ntile, nkp, nxt);
+        if (g >= 2) umma::mbar_wait(&bars->a_empty[b], ((g >> 1) - 1u) & 1u);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int row = 4 * (wl + WR_LOADERS * it) + rsub;
+          if (P.relu_in) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cur[it][u] = fmaxf(cur[it][u], 0.f);
+          }
+          wide_store_chunk<MODE>(a_base + b * CH_PANEL + row * 128 + ((ch ^ (row & 7)) << 4), cur[it]);
+        }
+        umma::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&bars->a_full[b]);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+#pragma unroll
+          for (int u = 0; u < 8; ++u) cur[it][u] = nxt[it][u];
+      }
+    }
+  } else {
+    // ---------------- epilogue warps (8): two per TMEM lane quarter, each owns two 16-column quarters of every panel
+    const int we = warp - 2 - WR_LOADERS;      // 0..7
+    const int q = warp & 3;                    // TMEM lane quarter = warp id % 4
+    const int half = we >> 2;                  // which of the quarter's two warps
+    const int lr = lane >> 2, lc = lane & 3;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int npan = (P.n + 63) >> 6;
+    uint32_t t = 0;
+    for (int tile = tile_lo; tile < tile_hi; ++tile, ++t) {
+      const uint32_t acc = t & 1u;
+      const long long l0 = (long long)tile * CH_TILE_M;
+      umma::mbar_wait(&bars->acc_full[acc], (t >> 1) & 1u);
+      umma::tc_fence_after();
+      const uint32_t tmem_s = tmem_base + acc * 256u;
+      const float *gbp = P.gbias ? P.gbias + (size_t)(l0 / P.gbias_rows) * P.n : nullptr;
+#pragma unroll 1
+      for (int pn = 0; pn < npan; ++pn) {
+#pragma unroll 1
+        for (int cqq = 0; cqq < 2; ++cqq) {
+          const int cb = pn * 64 + (2 * half + cqq) * 16;
+          if (cb >= P.n) continue;  // warp-uniform
+          uint32_t v[2][8];
+          umma::tmem_ld_16x256b_x2(tmem_s + lane_base + cb, v[0]);
+          umma::tmem_ld_16x256b_x2(tmem_s + lane_base + (16u << 16) + cb, v[1]);
+          float2 gb[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+          if (gbp) {
+            gb[0] = __ldg(reinterpret_cast<const float2 *>(gbp + cb + 2 * lc));
+            gb[1] = __ldg(reinterpret_cast<const float2 *>(gbp + cb + 8 + 2 * lc));
+          }
+          umma::tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int col = cb + 8 * i + 2 * lc;
+            const float sc0 = s_scale[col], sc1 = s_scale[col + 1], sh0 = s_shift[col], sh1 = s_shift[col + 1];
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const long long row = l0 + q * 32 + lr + 8 * j;
+              float y0 = __fmaf_rn(sc0, __uint_as_float(v[j >> 1][4 * i + 2 * (j & 1)]) + gb[i].x, sh0);
+              float y1 = __fmaf_rn(sc1, __uint_as_float(v[j >> 1][4 * i + 2 * (j & 1) + 1]) + gb[i].y, sh1);
+              if (P.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+              if (row < P.R) {
+                m0 = fmaxf(m0, y0); m1 = fmaxf(m1, y1);
+                if (P.out) {
+                  float *o = P.out + (size_t)row * P.ldo + P.out_col0 + col;
+                  if (col < P.n_valid) o[0] = y0;
+                  if (col + 1 < P.n_valid) o[1] = y1;
+                }
+              }
+            }
+            if (P.out_pool) {
+#pragma unroll
+              for (int off = 4; off <= 16; off <<= 1) {
+                m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, off));
+                m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, off));
+              }
+              if (lr == 0 && m0 > -INFINITY) {
+                float *o = P.out_pool + (size_t)(l0 / P.pool_rows) * P.n_valid + col;
+                if (col < P.n_valid) atomic_max_float(o, m0);
+                if (col + 1 < P.n_valid) atomic_max_float(o + 1, m1);
+              }
+            }
+          }
+        }
+      }
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&bars->acc_empty[acc]);
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    umma::tc_fence_after();
+    umma::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // pack one weight stage set: W (n_valid rows, ld columns) f32 row-major, columns [col0, col0 + K) are the K operand;
 // rows [row0, row0 + n_valid) of W map to stage rows 0..n_valid-1, rows up to n_pad are zero.
 // -> for every k panel: hi image [n_pad rows][64 k] K-major 128B-swizzled (then the lo image in x3 mode)
@@ -806,6 +1091,39 @@ extern "C" int rfd_mlp_chain_rows(int mode, const float *x_pm, int ldi, int B, i
   const ChainPlan p = chain_plan(mode, K0, 0, C1, C2, C3);
   if (!p.ok) return RFD_ERR_UNSUPPORTED_SIZE;
   if (out_pm && ldo < out_col0 + p.out_C) return RFD_ERR_INVALID_ARGUMENT;
+  if (p.nsteps == 1) {
+    // one layer (<= 256 outputs): the K-pipelined, role-split kernel; (B, L) rows are one flat list of B*L rows
+    const long long R = (long long)B * L, nt = (R + CH_TILE_M - 1) / CH_TILE_M;
+    if (nt > 0x7fffffffLL) return RFD_ERR_UNSUPPORTED_SIZE;
+    const uint8_t *base = reinterpret_cast<const uint8_t *>(packed);
+    WideParams W = {};
+    W.x = x_pm; W.ldi = ldi; W.K = K0; W.kp = p.st[0].kp; W.R = (int)R;
+    W.w = base;
+    W.scale = reinterpret_cast<const float *>(base + chain_off_scale(p));
+    W.shift = reinterpret_cast<const float *>(base + chain_off_shift(p));
+    W.n = p.st[0].n; W.n_valid = p.st[0].out_valid; W.relu = relu_last; W.relu_in = relu_in;
+    W.gbias = gbias; W.gbias_rows = gbias_rows;
+    W.out = out_pm; W.ldo = ldo; W.out_col0 = out_col0;
+    W.out_pool = out_pool; W.pool_rows = pool_rows;
+    W.num_tiles = (int)nt;
+    int dev = 0, sms = 148;
+    RFD_CHECK_CUDA(cudaGetDevice(&dev), "wide_rows getdevice");
+    RFD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "wide_rows sms");
+    const int grid = (int)(nt < sms ? nt : sms);
+    cudaStream_t st = as_stream(stream);
+#define RFD_WIDE_LAUNCH(MODE)                                                                                       \
+  do {                                                                                                              \
+    RFD_CHECK_CUDA(cudaFuncSetAttribute(wide_rows_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                        WR_SMEM_BYTES), "wide_rows attr");                                          \
+    wide_rows_kernel<MODE><<<grid, WR_THREADS, WR_SMEM_BYTES, st>>>(W);                                             \
+  } while (0)
+    if (mode == CH_MODE_BF16) RFD_WIDE_LAUNCH(CH_MODE_BF16);
+    else if (mode == CH_MODE_F16) RFD_WIDE_LAUNCH(CH_MODE_F16);
+    else RFD_WIDE_LAUNCH(CH_MODE_F16X3);
+#undef RFD_WIDE_LAUNCH
+    RFD_CHECK_LAUNCH("wide_rows_kernel");
+    return RFD_OK;
+  }
   ChainParams P = {};
   P.x_pm = x_pm; P.ldi = ldi; P.K0 = K0; P.M = L; P.S = 1;
   P.ldo = out_pm ? ldo : p.out_C; P.out_col0 = out_col0; P.pool_pm = 1;

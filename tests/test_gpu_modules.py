@@ -386,6 +386,15 @@ def test_chain_ex_relu_in_group_bias_and_epilogue_pool(mode):
     assert float((out[0, :, 8:8 + C] - ref.t()).abs().max()) <= tol
     assert bool((out[0, :, :8] == -3.0).all()) and bool((out[0, :, 8 + C:] == -3.0).all())      # nothing else touched
     assert pooled.shape == (1, G, C) and float((pooled[0] - ref_pool.t()).abs().max()) <= tol
+    # ragged row count (last tile partly empty), narrow operand and output, many tiles per CTA
+    Rr = 148 * 128 * 3 + 77
+    xs = torch.randn(1, Rr, 40, generator=g).to(DEV)
+    Ws, ss, ts = W[:24, :40].contiguous(), s[:24].contiguous(), t[:24].contiguous()
+    small = mlp.WideLayer(Ws, ss, ts, True, mode)
+    outs = torch.empty((1, Rr, 24), device=DEV)
+    small(xs, out=outs)
+    refs = torch.relu((xs[0] @ Ws.t()) * ss[None] + ts[None])
+    assert float((outs[0] - refs).abs().max()) <= (2e-5 if mode == "x3" else 5e-3) * max(1.0, float(refs.abs().max()))
     # pooled-only call (no rows written), ReLU output
     layer2 = mlp.WideLayer(W, s, t, True, mode)
     pooled2 = layer2(xr, out=None, pool_rows=rows)
