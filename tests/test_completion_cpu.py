@@ -167,3 +167,18 @@ def test_fast_encoder_algebra_on_cpu(monkeypatch):
     assert torch.equal(mask, mask_ref)
     assert out.shape == ref.shape == (B, 64, K)
     assert float((out - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_heading_angles_match_class2angle():
+    """pipeline.SceneGeneration.heading_angles == network.py:112-117 + configs/scannet_config.py:55-63 (class2angle_cuda)."""
+    import math
+    import torch
+    from rfdnet_b200.pipeline import SceneGeneration
+    g = torch.Generator().manual_seed(3)
+    ep = {"heading_scores": torch.randn(2, 50, 12, generator=g), "heading_residuals_normalized": torch.randn(2, 50, 12, generator=g) * 0.4}
+    got = SceneGeneration.heading_angles(ep, 12)
+    cls = torch.argmax(ep["heading_scores"], -1)
+    res = torch.gather(ep["heading_residuals_normalized"] * (math.pi / 12), 2, cls.unsqueeze(-1)).squeeze(2)
+    angle = cls.float() * (2 * math.pi / 12.0) + res
+    want = angle - 2 * math.pi * (angle > math.pi).float()
+    assert torch.equal(got, want) and float(got.max()) <= math.pi
