@@ -31,6 +31,21 @@ int main(void) {
   EXPECT(rfd_pointwise_mlp_f32(NULL, NULL, NULL, NULL, NULL, 1, 1, 1, 4, 4, 16, NULL, NULL) == RFD_ERR_INVALID_ARGUMENT);
   EXPECT(rfd_onet_decode(NULL, 0, 1, 128, NULL, NULL, 1, NULL, NULL, 0.f, NULL, NULL) == RFD_ERR_INVALID_ARGUMENT);
   EXPECT(rfd_mlp_chain(RFD_MLP_MODE_F16X3, NULL, 1, 4, 128, NULL, 64, 64, 128, 1, 16, NULL, NULL, NULL) == RFD_ERR_INVALID_ARGUMENT);
+  /* round-2 entry points: surface extraction, STN_Group, the extended chain calls */
+  EXPECT(rfd_extract_mesh(NULL, 1, 32, 0.0, 1.1, NULL, 0, NULL, 16, 16, NULL, NULL, NULL) == RFD_ERR_INVALID_ARGUMENT);
+  EXPECT(rfd_extract_mesh((const float *)16, 1, 40, 0.0, 1.1, (void *)16, 0, (int *)16, 16, 16, (int *)16, (unsigned long long *)16, NULL) ==
+         RFD_ERR_UNSUPPORTED_SIZE); /* the padded lattice must fit in shared memory: R <= 32 */
+  EXPECT(rfd_extract_mesh(NULL, 0, 32, 0.0, 1.1, NULL, 0, NULL, 0, 0, NULL, NULL, NULL) == RFD_OK);
+  EXPECT(rfd_query_and_group_rotated((const float *)16, (const float *)16, NULL, NULL, 1, 8, 8, 0, 0.1f, 4, 1, 0, (float *)16, NULL, NULL,
+                                     NULL) == RFD_ERR_INVALID_ARGUMENT); /* heading missing */
+  EXPECT(rfd_stn_apply(NULL, NULL, 1, 4, 64, NULL, NULL) == RFD_ERR_INVALID_ARGUMENT);
+  EXPECT(rfd_stn_apply(NULL, NULL, 0, 4, 64, NULL, NULL) == RFD_OK);
+  EXPECT(rfd_mlp_chain_ex(RFD_MLP_MODE_F16X3, (const float *)16, 1, 64, 256, (const void *)16, 64, 0, 0, 1, 1, (float *)16, NULL, 0,
+                          (const float *)16, 100, NULL, 0, NULL) == RFD_ERR_UNSUPPORTED_SIZE); /* group of 100 rows: not a tile multiple */
+  EXPECT(rfd_mlp_chain_rows(RFD_MLP_MODE_F16X3, (const float *)16, 66, 1, 64, 256, (const void *)16, 64, 0, 0, 1, (float *)16, 64, 0, 0,
+                            NULL, 0, NULL, 0, NULL) == RFD_ERR_INVALID_ARGUMENT); /* row stride must be a multiple of 4 floats */
+  EXPECT(rfd_mlp_chain_rows(RFD_MLP_MODE_F16X3, (const float *)16, 64, 1, 64, 256, (const void *)16, 64, 0, 0, 1, (float *)16, 32, 0, 0,
+                            NULL, 0, NULL, 0, NULL) == RFD_ERR_INVALID_ARGUMENT); /* output row narrower than the layer */
   /* empty work is a no-op success */
   EXPECT(rfd_furthest_point_sampling(NULL, 0, 16, 4, NULL, NULL) == RFD_OK);
   EXPECT(rfd_ball_query(NULL, NULL, 0, 8, 8, 0.1f, 4, NULL, NULL) == RFD_OK);
