@@ -11,7 +11,6 @@ normal estimation -- the reference's ISCNet config runs upsampling_steps = 0 and
 """
 import math
 
-import numpy as np
 import torch
 
 from . import _lib
